@@ -1,0 +1,443 @@
+"""CPU oracle for the GPEXP greedy experimental-design hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``gpexp_b200/`` may import this
+module; only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` use it, and only as the checker or as
+the timed CPU baseline.  The product path is CUDA-only.
+
+Two layers live here, both plain numpy float64:
+
+* ``ref_*``  -- a *faithful* restatement of the reference's algorithm: the same
+  per-row / per-candidate loops and the same ``np.linalg.pinv`` (SVD,
+  rcond=1e-15) solves, cited function by function against
+  ``/root/reference/gpExp/*.py`` (file:line in each docstring).  These are
+  what the reference would compute and (roughly) how long it would take.
+* ``fast_*`` -- the vectorised Cholesky / Schur-complement restatement (same
+  mathematics, O(n) less work per step) that the CUDA path mirrors.  It is
+  proven equal to ``ref_*`` on small cases (tests/test_oracle.py) and is the
+  checker at sizes ``ref_*`` cannot reach.
+
+Pinning: the reference ships no tests or golden vectors
+(``test/test_kernel.py:1-24`` is an empty licence header), so this oracle is
+pinned against outputs of the *unmodified reference itself*, imported in the
+build container by ``tests/golden/make_golden.py`` and frozen in
+``tests/golden/*.npz`` (indices, per-step scores, variances, Gram matrices).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+SE = 0
+MATERN32 = 1
+MEHLER = 2
+
+FAMILY_NAMES = {SE: "se", MATERN32: "matern32", MEHLER: "mehler"}
+
+
+# --------------------------------------------------------------------------
+# Covariance functions (pairwise semantics)            kernels.py:49-65
+# --------------------------------------------------------------------------
+@dataclass
+class KernelSpec:
+    """Family + hyper-parameters of one covariance function.
+
+    family SE        params: cl[d] (correlation lengths), signal   kernels.py:103-123
+    family MATERN32  params: rho, signal                           kernels.py:74-91
+    family MEHLER    params: t[d]                                  kernels.py:183-228, :250-293
+    """
+
+    family: int
+    dim: int
+    cl: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    signal: float = 1.0
+    rho: float = 1.0
+    t: np.ndarray = field(default_factory=lambda: np.zeros(0))
+
+    # ---- constructors mirroring the reference class constructors ----------
+    @staticmethod
+    def se(cl, signal, dim):
+        cl = np.asarray(cl, dtype=np.float64).ravel()
+        if cl.size == 1:  # kernels.py:106-107 isotropic -> tiled to d
+            cl = np.tile(cl, dim)
+        assert cl.size == dim
+        return KernelSpec(SE, dim, cl=cl.copy(), signal=float(signal))
+
+    @staticmethod
+    def matern32(rho, signal, dim):
+        return KernelSpec(MATERN32, dim, rho=float(rho), signal=float(signal))
+
+    @staticmethod
+    def mehler(t, dim):
+        t = np.asarray(t, dtype=np.float64).ravel()
+        assert t.size == dim
+        return KernelSpec(MEHLER, dim, t=t.copy())
+
+    # ---- evaluateF: equal-shaped inputs -> (p,) ---------------------------
+    def evaluateF(self, x1, x2):
+        assert x1.shape == x2.shape
+        if self.family == SE:  # kernels.py:121-122
+            return self.signal * np.exp(
+                -0.5 * np.sum((x1 - x2) ** 2.0 * self.cl ** -2.0, axis=1))
+        if self.family == MATERN32:  # kernels.py:87-89
+            d = np.sqrt(np.sum((x1 - x2) ** 2.0, axis=1))
+            term = np.sqrt(3) * d / self.rho
+            return self.signal * (1.0 + term) * np.exp(-term)
+        if self.family == MEHLER:  # kernels.py:223-227 product of 1-D, :282-285
+            out = np.ones(x1.shape[0])
+            for i in range(self.dim):
+                t = self.t[i]
+                a = x1[:, i]
+                b = x2[:, i]
+                out = out * ((1.0 - t ** 2.0) ** (-1.0 / 2.0) * np.exp(
+                    -(a ** 2.0 * t ** 2.0 - 2.0 * t * a * b + b ** 2.0 * t ** 2.0)
+                    / (2.0 * (1.0 - t ** 2.0))))
+            return out
+        raise ValueError("unknown kernel family")
+
+    # ---- evaluate: pairwise with (1,d) broadcast        kernels.py:49-65 --
+    def evaluate(self, x1, x2):
+        assert x1.ndim > 1 and x2.ndim > 1
+        assert x1.shape[1] == self.dim and x2.shape[1] == self.dim
+        n1, n2 = x1.shape[0], x2.shape[0]
+        if n1 > n2:
+            return self.evaluateF(x1, np.tile(x2, (n1, 1)))
+        if n1 < n2:
+            return self.evaluateF(np.tile(x1, (n2, 1)), x2)
+        return self.evaluateF(x1, x2)
+
+    # ---- vectorised cross-Gram K[i,j] = k(X[i], Y[j]) ----------------------
+    def gram(self, X, Y):
+        """Same per-element formula as evaluateF, broadcast to (nx, ny)."""
+        X = np.asarray(X, dtype=np.float64)
+        Y = np.asarray(Y, dtype=np.float64)
+        if self.family == SE:
+            acc = np.zeros((X.shape[0], Y.shape[0]))
+            for i in range(self.dim):
+                diff = X[:, i:i + 1] - Y[None, :, i]
+                acc += diff ** 2.0 * self.cl[i] ** -2.0
+            return self.signal * np.exp(-0.5 * acc)
+        if self.family == MATERN32:
+            acc = np.zeros((X.shape[0], Y.shape[0]))
+            for i in range(self.dim):
+                diff = X[:, i:i + 1] - Y[None, :, i]
+                acc += diff ** 2.0
+            term = np.sqrt(3) * np.sqrt(acc) / self.rho
+            return self.signal * (1.0 + term) * np.exp(-term)
+        if self.family == MEHLER:
+            out = np.ones((X.shape[0], Y.shape[0]))
+            for i in range(self.dim):
+                t = self.t[i]
+                a = X[:, i:i + 1]
+                b = Y[None, :, i]
+                out = out * ((1.0 - t ** 2.0) ** (-1.0 / 2.0) * np.exp(
+                    -(a ** 2.0 * t ** 2.0 - 2.0 * t * a * b + b ** 2.0 * t ** 2.0)
+                    / (2.0 * (1.0 - t ** 2.0))))
+            return out
+        raise ValueError("unknown kernel family")
+
+    def prior(self, X):
+        """k(x, x) per point (no noise)."""
+        return self.evaluateF(X, X)
+
+    def packed_params(self):
+        """Flat parameter vector in the order the C ABI expects (include/gpexp_b200.h)."""
+        if self.family == SE:
+            return np.concatenate([self.cl, [self.signal]])
+        if self.family == MATERN32:
+            return np.array([self.rho, self.signal])
+        return self.t.copy()
+
+
+# --------------------------------------------------------------------------
+# Faithful restatement of the reference (loops + pinv)
+# --------------------------------------------------------------------------
+def ref_covariance_matrix(kern: KernelSpec, points, nugget=0.0):
+    """gp_kernel_utilities.py:34-68 -- row loop of pairwise evaluates + diag(nugget)."""
+    n, dim = points.shape
+    cov = np.zeros((n, n))
+    for j in range(n):
+        cov[j, :] = kern.evaluate(points, points[j].reshape(1, dim))
+    if isinstance(nugget, float):
+        dadd = nugget * np.ones(n)
+    elif isinstance(nugget, np.ndarray):
+        dadd = nugget[:]
+    else:  # the reference raises NameError here (gp_kernel_utilities.py:62-67)
+        raise NameError("nugget must be float or ndarray")
+    return cov + np.diag(dadd)
+
+
+def ref_add_nodes(kern, nodes, noise):
+    """gp.py:176-181 -- covariance + pinv precision."""
+    cov = ref_covariance_matrix(kern, nodes, noise)
+    return cov, np.linalg.pinv(cov)
+
+
+def ref_evaluate_variance(kern, nodes, precision, newpt):
+    """gp.py:246-256 -- M x n kernel values, python loop over query points, raw (signed) variance."""
+    m, n = newpt.shape[0], nodes.shape[0]
+    kv = np.zeros((m, n))
+    for j in range(n):
+        kv[:, j] = kern.evaluate(newpt, nodes[j].reshape(1, kern.dim))
+    var_new = kern.evaluate(newpt, newpt)
+    var = np.zeros(m)
+    for j in range(m):
+        var[j] = var_new[j] - np.dot(kv[j, :], np.dot(precision, kv[j, :].T))
+    return var
+
+
+def ref_ivar_cost(kern, design, mc, noise):
+    """experimentalDesign.py:105-117 -- |mean posterior variance over the MC points|.
+
+    ``noise`` is a float (homoscedastic gp.noise) or an ndarray of per-point
+    nuggets (the space.noiseFunc branch, :110-114).
+    """
+    _, prec = ref_add_nodes(kern, design, noise)
+    var_mc = ref_evaluate_variance(kern, design, prec, mc)
+    return abs(1.0 / float(mc.shape[0]) * np.sum(var_mc))
+
+
+def ref_greedy_var(kern, pool, n_points, weights=None, ind_keep_start=()):
+    """experimentalDesign.py:787-845 -- greedy max posterior variance, nugget 0, pinv each step.
+
+    Returns (indices, list of per-step score vectors).  The reference returns
+    pool[indices]; indices are what the parity tests compare.
+    """
+    ind = list(ind_keep_start)
+    have = len(ind)
+    dim = pool.shape[1]
+    c = pool.shape[0]
+    scores = []
+    while have < n_points:
+        if have == 0:
+            k = kern.evaluate(pool, pool)  # :816
+        else:
+            cov = ref_covariance_matrix(kern, pool[ind, :])  # :825 nugget 0.0
+            inv = np.linalg.pinv(cov)  # :826
+            kv = np.zeros((have, c))
+            for i in range(have):  # :829-831
+                kv[i, :] = kern.evaluate(pool, pool[ind[i]].reshape(1, dim))
+            k = np.zeros(c)
+            for i in range(c):  # :834-837
+                pt = pool[i].reshape(1, dim)
+                k[i] = (kern.evaluate(pt, pt) - np.dot(kv[:, i].T, np.dot(inv, kv[:, i])))[0]
+        if weights is not None:
+            k = k * weights
+        scores.append(k.copy())
+        ind.append(int(np.argmax(k)))  # :821 / :841 first maximum
+        have += 1
+    return ind, scores
+
+
+def ref_greedy_ivar(kern, cand, mc, n_points, noise, cand_subset=None):
+    """Discrete greedy IVAR as SURVEY.md section 8(c) defines it (the reference has the
+    cost function, experimentalDesign.py:79-117, but no discrete driver): at each step
+    evaluate the reference IVAR cost of design+{c} for every candidate c and take
+    np.argmin.  Returns (indices, per-step cost vectors)."""
+    ind = []
+    costs = []
+    cs = range(cand.shape[0]) if cand_subset is None else cand_subset
+    for _ in range(n_points):
+        cost = np.full(cand.shape[0], np.inf)
+        for c in cs:
+            pts = np.vstack([cand[ind, :], cand[c:c + 1, :]])
+            cost[c] = ref_ivar_cost(kern, pts, mc, noise)
+        costs.append(cost)
+        ind.append(int(np.argmin(cost)))
+    return ind, costs
+
+
+def ref_mi_cost(kern, pool, noise, index, index_added):
+    """experimentalDesign.py:252-285 -- var(y|A) / var(y|V minus A minus y), two pinv's."""
+    dim = pool.shape[1]
+    point = pool[index, :].reshape(1, dim)
+    var = kern.evaluate(point, point)
+    added = pool[index_added, :].reshape(len(index_added), dim)
+    kva = kern.evaluate(added, point)
+    cov_num = ref_covariance_matrix(kern, added, noise)
+    numerator = var - np.dot(kva.T, np.dot(np.linalg.pinv(cov_num), kva))
+    left = np.setdiff1d(np.arange(pool.shape[0]), index_added)
+    left = np.setdiff1d(left, [index])
+    pts_left = pool[left, :]
+    kvl = kern.evaluate(pts_left, point)
+    cov_den = ref_covariance_matrix(kern, pts_left, noise)
+    denominator = var - np.dot(kvl.T, np.dot(np.linalg.pinv(cov_den), kvl))
+    return numerator / denominator
+
+
+def ref_greedy_mi(kern, pool, noise, n_points, start=0):
+    """experimentalDesign.py:753-785.  Returns (indices, per-step score vectors over the
+    remaining options, per-step option index arrays)."""
+    ind = [start]
+    options = np.setdiff1d(np.arange(pool.shape[0]), ind)
+    scores, opts = [], []
+    for _ in range(len(ind), n_points):
+        out = np.zeros(len(options))
+        for j, i in enumerate(options):
+            out[j] = ref_mi_cost(kern, pool, noise, int(i), ind)[0]
+        scores.append(out)
+        opts.append(options.copy())
+        new = int(options[np.argmax(out)])
+        ind.append(new)
+        options = np.setdiff1d(options, new)
+    return ind, scores, opts
+
+
+# --------------------------------------------------------------------------
+# Vectorised Cholesky / Schur restatement (what the CUDA path mirrors)
+# --------------------------------------------------------------------------
+def fast_posterior_variance(kern, design, x, noise=0.0):
+    """var[j] = k(x_j,x_j) - |L^-1 k(D,x_j)|^2 with K_DD + diag(noise) = L L^T.
+    Equals ref_evaluate_variance up to cond(K)*eps (gp.py:251-255)."""
+    from scipy.linalg import solve_triangular
+    n = design.shape[0]
+    nug = noise * np.ones(n) if np.isscalar(noise) else np.asarray(noise)
+    kdd = kern.gram(design, design) + np.diag(nug)
+    low = np.linalg.cholesky(kdd)
+    w = solve_triangular(low, kern.gram(design, x), lower=True)
+    return kern.prior(x) - np.sum(w * w, axis=0)
+
+
+def fast_greedy_var(kern, pool, n_points, weights=None, ind_keep_start=()):
+    """Greedy max-variance == diagonally pivoted Cholesky of K_CC.
+
+    W[n,:] = (k(x_p,.) - W[:n,p]^T W[:n,:]) / sqrt(var[p]) ; var -= W[n,:]^2.
+    Seeds in ind_keep_start are forced pivots.  Returns (indices, per-step scores).
+    """
+    c = pool.shape[0]
+    var = kern.prior(pool).copy()
+    w = np.zeros((n_points, c))
+    ind, scores = [], []
+
+    def append(p):
+        n = len(ind)
+        row = kern.gram(pool[p:p + 1], pool)[0] - w[:n, p] @ w[:n, :]
+        row /= math.sqrt(var[p])
+        w[n, :] = row
+        var[:] = var - row * row
+        ind.append(int(p))
+
+    for p in ind_keep_start:
+        append(p)
+    while len(ind) < n_points:
+        k = var * weights if weights is not None else var
+        scores.append(k.copy())
+        append(int(np.argmax(k)))
+    return ind, scores
+
+
+def fast_ivar_scores(kern, cand, mc, w_m, var_m, w_c, var_c, noise, block=4096):
+    """IVAR cost of design+{c} for every candidate c via the Schur identity:
+
+        cost[c] = | mean_m var_D(m) - (1/M) sum_m cov_D(m,c)^2 / (var_D(c) + noise) |
+        cov_D(m,c) = k(m,c) - W_M[:,m] . W_C[:,c]
+
+    The reduction is 0 where var_D(c)+noise is numerically zero (SURVEY.md section 7,
+    duplicate-candidate rule: pinv drops the null direction)."""
+    m = mc.shape[0]
+    c = cand.shape[0]
+    base = np.sum(var_m) / m
+    r = np.zeros(c)
+    for c0 in range(0, c, block):
+        cov = kern.gram(mc, cand[c0:c0 + block]) - w_m.T @ w_c[:, c0:c0 + block]
+        r[c0:c0 + block] = np.sum(cov * cov, axis=0)
+    den = var_c + noise
+    tiny = den <= ZERO_VAR_TOL * kern_scale(kern, cand)
+    red = np.where(tiny, 0.0, r / np.where(tiny, 1.0, den) / m)
+    return np.abs(base - red)
+
+
+ZERO_VAR_TOL = 1e-13
+
+
+def kern_scale(kern, pts):
+    """Magnitude of the prior variance, used only to decide 'numerically zero'."""
+    return float(np.max(np.abs(kern.prior(pts[:1])))) if pts.shape[0] else 1.0
+
+
+def fast_greedy_ivar(kern, cand, mc, n_points, noise):
+    """Incremental greedy IVAR: append one row to W_M and W_C per step with
+    divisor sqrt(var_D(p)+noise), running var updates.  Returns (indices, per-step costs)."""
+    c, m = cand.shape[0], mc.shape[0]
+    w_c = np.zeros((n_points, c))
+    w_m = np.zeros((n_points, m))
+    var_c = kern.prior(cand).copy()
+    var_m = kern.prior(mc).copy()
+    ind, costs = [], []
+    for n in range(n_points):
+        cost = fast_ivar_scores(kern, cand, mc, w_m[:n], var_m, w_c[:n], var_c, noise)
+        costs.append(cost)
+        p = int(np.argmin(cost))
+        lnn = math.sqrt(var_c[p] + noise)
+        col = w_c[:n, p].copy()
+        row_c = (kern.gram(cand[p:p + 1], cand)[0] - col @ w_c[:n, :]) / lnn
+        row_m = (kern.gram(cand[p:p + 1], mc)[0] - col @ w_m[:n, :]) / lnn
+        w_c[n, :] = row_c
+        w_m[n, :] = row_m
+        var_c -= row_c * row_c
+        var_m -= row_m * row_m
+        ind.append(p)
+    return ind, costs
+
+
+def fast_greedy_mi(kern, pool, noise, n_points, start=0):
+    """Greedy MI with the exact restatement of SURVEY.md 3.3:
+
+        numerator(y)   = var(y | A)                 (incremental pivoted-Cholesky rows, nugget=noise)
+        denominator(y) = 1 / [(K_SS + noise I)^-1]_yy - noise,   S = V minus A  (y in S)
+
+    and a rank-1 downdate of the precision when a point leaves S.  Returns
+    (indices, per-step score vectors of length |V| with selected entries = -inf)."""
+    v = pool.shape[0]
+    kvv = kern.gram(pool, pool) + noise * np.eye(v)
+    prec = np.linalg.inv(kvv)
+    prior = kern.prior(pool)
+    num = prior.copy()
+    w = np.zeros((n_points, v))
+    selected = np.zeros(v, dtype=bool)
+    ind, scores = [], []
+    pd = np.diag(prec).copy()
+    us = []
+
+    def current_col(p):
+        col = prec[:, p].copy()
+        for u in us:
+            col -= u * u[p]
+        return col
+
+    def take(p):
+        nonlocal pd
+        n = len(ind)
+        lnn = math.sqrt(num[p] + noise)
+        row = (kern.gram(pool[p:p + 1], pool)[0] - w[:n, p] @ w[:n, :]) / lnn
+        w[n, :] = row
+        num[:] = num - row * row
+        col = current_col(p)
+        u = col / math.sqrt(col[p])
+        us.append(u)
+        pd = pd - u * u
+        selected[p] = True
+        ind.append(int(p))
+
+    take(start)
+    while len(ind) < n_points:
+        den = 1.0 / np.where(selected, 1.0, pd) - noise
+        s = np.where(selected, -np.inf, num / den)
+        scores.append(s)
+        take(int(np.argmax(s)))
+    return ind, scores
+
+
+# --------------------------------------------------------------------------
+# Convenience: build W / var state for a *given* design (used by tests + bench baseline)
+# --------------------------------------------------------------------------
+def fast_design_state(kern, design, x, noise):
+    from scipy.linalg import solve_triangular
+    n = design.shape[0]
+    if n == 0:
+        return np.zeros((0, x.shape[0])), kern.prior(x).copy()
+    low = np.linalg.cholesky(kern.gram(design, design) + noise * np.eye(n))
+    w = solve_triangular(low, kern.gram(design, x), lower=True)
+    return w, kern.prior(x) - np.sum(w * w, axis=0)

@@ -1,0 +1,248 @@
+"""Generate the golden vectors in tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container only (the reference is mounted read-only at /root/reference and
+does not exist on the GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+The reference has no tests of its own (test/test_kernel.py:1-24 is an empty header), so these
+files are what pins both the CPU oracle (oracle/gpexp_oracle.py) and the CUDA path.  Every array
+below is an output of reference code (gpExp.kernels / gpExp.gp / gpExp.gp_kernel_utilities /
+gpExp.experimentalDesign) on seeded numpy inputs; the inputs are stored next to the outputs.
+numpy 2.3.5 / scipy 1.18.1 / OpenBLAS 0.3.30 were used.
+"""
+import io
+import os
+import sys
+import warnings
+from contextlib import redirect_stdout
+
+import numpy as np
+
+sys.dont_write_bytecode = True
+sys.path.insert(0, "/root/reference")
+warnings.filterwarnings("ignore", category=DeprecationWarning)
+
+import gpExp.kernels as rk  # noqa: E402
+import gpExp.gp as rgp  # noqa: E402
+import gpExp.gp_kernel_utilities as rku  # noqa: E402
+import gpExp.experimentalDesign as red  # noqa: E402
+from gpExp.approximation import Space  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def mk_kernel(name):
+    if name == "se_iso_1d":
+        return rk.KernelSquaredExponential([0.05], 1.0, 1), 1
+    if name == "se_ard_2d":
+        return rk.KernelSquaredExponential([0.06, 0.09], 1.0, 2), 2
+    if name == "se_ard_2d_wide":
+        return rk.KernelSquaredExponential([0.3, 0.45], 1.7, 2), 2
+    if name == "se_ard_10d":
+        return rk.KernelSquaredExponential(list(np.linspace(0.5, 1.5, 10)), 1.0, 10), 10
+    if name == "matern_5d":
+        return rk.KernelIsoMatern(1.0, 1.0, 5), 5
+    if name == "matern_5d_b":
+        return rk.KernelIsoMatern(0.5, 2.5, 5), 5
+    if name == "mehler_3d":
+        return rk.KernelMehlerND([0.9, 0.9, 0.9], 3), 3
+    if name == "mehler_3d_b":
+        return rk.KernelMehlerND([0.5, 0.7, 0.3], 3), 3
+    if name == "mehler_1d":
+        return rk.KernelMehler1D(0.6, 1), 1
+    raise KeyError(name)
+
+
+KERNELS = ["se_iso_1d", "se_ard_2d", "se_ard_2d_wide", "se_ard_10d", "matern_5d", "matern_5d_b",
+           "mehler_3d", "mehler_3d_b", "mehler_1d"]
+
+
+def sample(rng, name, n, d):
+    if name.startswith("mehler"):
+        return rng.standard_normal((n, d))
+    return rng.uniform(-1.0, 1.0, (n, d))
+
+
+def quiet(fn, *a, **k):
+    with redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def match_rows(points, pool):
+    """Recover indices from the rows the reference returns (it returns points, not indices)."""
+    out = []
+    for p in points:
+        hit = np.where(np.all(pool == p, axis=1))[0]
+        out.append(int(hit[0]))
+    return np.array(out, dtype=np.int64)
+
+
+def gen_kernels(out):
+    rng = np.random.default_rng(101)
+    for name in KERNELS:
+        kern, d = mk_kernel(name)
+        x1 = sample(rng, name, 57, d)
+        x2 = sample(rng, name, 57, d)
+        one = sample(rng, name, 1, d)
+        out[f"kern/{name}/x1"] = x1
+        out[f"kern/{name}/x2"] = x2
+        out[f"kern/{name}/one"] = one
+        out[f"kern/{name}/pair"] = kern.evaluate(x1, x2)
+        out[f"kern/{name}/bcast_right"] = kern.evaluate(x1, one)
+        out[f"kern/{name}/bcast_left"] = kern.evaluate(one, x2)
+        out[f"kern/{name}/prior"] = kern.evaluate(x1, x1)
+
+
+def gen_gram(out):
+    rng = np.random.default_rng(102)
+    for name in ["se_ard_2d", "se_ard_10d", "matern_5d", "mehler_3d_b"]:
+        kern, d = mk_kernel(name)
+        pts = sample(rng, name, 45, d)
+        nug = rng.uniform(1e-4, 1e-2, 45)
+        out[f"gram/{name}/pts"] = pts
+        out[f"gram/{name}/nugvec"] = nug
+        out[f"gram/{name}/K0"] = rku.calculateCovarianceMatrix(kern, pts)
+        out[f"gram/{name}/Kscalar"] = rku.calculateCovarianceMatrix(kern, pts, 1e-3)
+        out[f"gram/{name}/Kvec"] = rku.calculateCovarianceMatrix(kern, pts, nug)
+
+
+def gen_gp(out):
+    rng = np.random.default_rng(103)
+    for name, noise in [("se_ard_2d_wide", 1e-6), ("matern_5d", 0.0), ("mehler_3d", 1e-2), ("se_ard_10d", 1e-6)]:
+        kern, d = mk_kernel(name)
+        nodes = sample(rng, name, 40, d)
+        query = np.vstack([sample(rng, name, 297, d), nodes[:3]])
+        fvals = np.sin(nodes.sum(axis=1))
+        gp = rgp.GP(kern, noise)
+        gp.train(nodes, fvals)
+        var = gp.evaluateVariance(query, parallel=0)
+        mean, absvar = gp.evaluate(query, compvar=1)
+        mean2, cov = gp.evaluate(query[:25], compvar=2)
+        out[f"gp/{name}/nodes"] = nodes
+        out[f"gp/{name}/query"] = query
+        out[f"gp/{name}/fvals"] = fvals
+        out[f"gp/{name}/noise"] = np.float64(noise)
+        out[f"gp/{name}/cov"] = gp.covarianceMatrix
+        out[f"gp/{name}/prec"] = gp.precisionMatrix
+        out[f"gp/{name}/coeff"] = gp.coeff
+        out[f"gp/{name}/var"] = var
+        out[f"gp/{name}/mean"] = mean
+        out[f"gp/{name}/absvar"] = absvar
+        out[f"gp/{name}/cov25"] = cov
+        out[f"gp/{name}/cond"] = np.float64(np.linalg.cond(gp.covarianceMatrix))
+        # IVAR cost of this design (experimentalDesign.py:79-117), homoscedastic
+        space = Space(d, None, None, noise=None)
+        mc = sample(rng, name, 1500, d)
+        cf = red.costFunctionGP_IVAR(gp, 40, space, mcPoints=mc)
+        out[f"gp/{name}/mc"] = mc
+        out[f"gp/{name}/ivar_cost"] = np.float64(cf.evaluate(nodes))
+    # heteroscedastic branch (:110-114): per-point nugget from space.noiseFunc
+    kern, d = mk_kernel("se_ard_2d_wide")
+    nodes = sample(rng, "se", 25, d)
+    mc = sample(rng, "se", 1000, d)
+    nf = lambda p: 1e-4 + 1e-3 * (p[:, 0] ** 2)  # noqa: E731
+    space = Space(d, None, None, noise=nf)
+    cf = red.costFunctionGP_IVAR(rgp.GP(kern, 1e-6), 25, space, mcPoints=mc)
+    out["gp/hetero/nodes"] = nodes
+    out["gp/hetero/mc"] = mc
+    out["gp/hetero/ivar_cost"] = np.float64(cf.evaluate(nodes))
+
+
+def gen_greedy_var(out):
+    rng = np.random.default_rng(104)
+    cases = [("se_iso_1d", 300, 12, False, []), ("matern_5d", 400, 30, False, []),
+             ("mehler_3d_b", 250, 10, True, []), ("se_ard_2d", 350, 25, True, [7, 3]),
+             ("se_ard_10d", 300, 20, False, [])]
+    for ci, (name, c, n, use_w, seeds) in enumerate(cases):
+        kern, d = mk_kernel(name)
+        pool = sample(rng, name, c, d)
+        w = rng.uniform(0.5, 1.5, c) if use_w else None
+        pts = quiet(red.performGreedyVarExperimentalDesign, kern, pool, n, d, weights=w,
+                    indKeepStart=list(seeds))
+        idx = match_rows(pts, pool)
+        # per-step scores from the reference GP (same k(x,x) - k^T pinv(K) k, nugget 0.0)
+        scores = np.zeros((n, c))
+        for step in range(len(seeds), n):
+            if step == 0:
+                k = kern.evaluate(pool, pool)
+            else:
+                gp = rgp.GP(kern, 0.0)
+                gp.addNodesAndComputeCovariance(pool[idx[:step]])
+                k = gp.evaluateVariance(pool, parallel=0)
+            scores[step] = k * w if use_w else k
+        out[f"gvar/{ci}/name"] = np.array(name)
+        out[f"gvar/{ci}/pool"] = pool
+        out[f"gvar/{ci}/weights"] = w if use_w else np.zeros(0)
+        out[f"gvar/{ci}/seeds"] = np.array(seeds, dtype=np.int64)
+        out[f"gvar/{ci}/idx"] = idx
+        out[f"gvar/{ci}/scores"] = scores
+
+
+def gen_greedy_ivar(out):
+    rng = np.random.default_rng(105)
+    cases = [("se_iso_1d", 80, 1000, 8, 1e-6), ("se_ard_2d", 100, 1500, 10, 1e-6),
+             ("matern_5d", 90, 1200, 8, 1e-4), ("mehler_3d", 70, 1000, 6, 1e-2),
+             ("se_ard_2d_wide", 60, 800, 6, 0.0)]
+    for ci, (name, c, m, n, noise) in enumerate(cases):
+        kern, d = mk_kernel(name)
+        cand = sample(rng, name, c, d)
+        mc = sample(rng, name, m, d)
+        space = Space(d, None, None, noise=None)
+        gp = rgp.GP(kern, float(noise))
+        idx, costs, conds = [], np.zeros((n, c)), np.zeros(n)
+        for step in range(n):
+            cf = red.costFunctionGP_IVAR(gp, step + 1, space, mcPoints=mc)
+            for j in range(c):
+                costs[step, j] = cf.evaluate(np.vstack([cand[idx], cand[j:j + 1]]))
+            idx.append(int(np.argmin(costs[step])))
+            kd = rku.calculateCovarianceMatrix(kern, cand[idx], float(noise))
+            conds[step] = np.linalg.cond(kd)
+        out[f"givar/{ci}/name"] = np.array(name)
+        out[f"givar/{ci}/cand"] = cand
+        out[f"givar/{ci}/mc"] = mc
+        out[f"givar/{ci}/noise"] = np.float64(noise)
+        out[f"givar/{ci}/idx"] = np.array(idx, dtype=np.int64)
+        out[f"givar/{ci}/costs"] = costs
+        out[f"givar/{ci}/cond"] = conds
+
+
+def gen_greedy_mi(out):
+    rng = np.random.default_rng(106)
+    cases = [("mehler_3d", 80, 8, 1e-2, 0), ("matern_5d", 60, 7, 1e-3, 5), ("se_ard_2d_wide", 50, 6, 1e-2, 0)]
+    for ci, (name, v, n, noise, start) in enumerate(cases):
+        kern, d = mk_kernel(name)
+        pool = sample(rng, name, v, d)
+        space = Space(d, None, None, noise=None)
+        gp = rgp.GP(kern, float(noise))
+        cf = red.costFunctionGP_MI(gp, n, space, nmc=v, mcpoints=pool)
+        pts = red.performGreedyMIExperimentalDesign(cf, n, start=start)
+        idx = match_rows(pts, pool)
+        scores = np.full((n, v), -np.inf)
+        for step in range(1, n):
+            for j in range(v):
+                if j in idx[:step]:
+                    continue
+                scores[step, j] = cf.evaluate(j, list(idx[:step]))[0]
+        out[f"gmi/{ci}/name"] = np.array(name)
+        out[f"gmi/{ci}/pool"] = pool
+        out[f"gmi/{ci}/noise"] = np.float64(noise)
+        out[f"gmi/{ci}/start"] = np.int64(start)
+        out[f"gmi/{ci}/idx"] = idx
+        out[f"gmi/{ci}/scores"] = scores
+        out[f"gmi/{ci}/cov"] = cf.cov
+        out[f"gmi/{ci}/invcov"] = cf.invcov
+
+
+def main():
+    for fname, gen in [("kernels.npz", gen_kernels), ("gram.npz", gen_gram), ("gp.npz", gen_gp),
+                       ("greedy_var.npz", gen_greedy_var), ("greedy_ivar.npz", gen_greedy_ivar),
+                       ("greedy_mi.npz", gen_greedy_mi)]:
+        out = {}
+        gen(out)
+        np.savez_compressed(os.path.join(HERE, fname), **out)
+        print(fname, len(out), "arrays", os.path.getsize(os.path.join(HERE, fname)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
