@@ -1,0 +1,632 @@
+// HBM-bound kernels of the greedy design path: covariance evaluation (K1), incremental row append with
+// running variance (K3+K4), arg-reduce with numpy tie-break (K7), pivot bookkeeping and the MI helpers (K6).
+#include <math.h>
+
+#include "gpx_common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// a1  pairwise k(X[j], Y[j]) with (1,d) broadcast                         kernels.py:49-65
+// ---------------------------------------------------------------------------------------------
+template <int FAM>
+__global__ void __launch_bounds__(256) pairwise_kernel(const __grid_constant__ KParams kp, const double* __restrict__ X,
+                                                        int64_t nx, int64_t ldx, const double* __restrict__ Y,
+                                                        int64_t ny, int64_t ldy, double* __restrict__ out, int64_t n) {
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= n) return;
+    const int64_t jx = nx == 1 ? 0 : j;
+    const int64_t jy = ny == 1 ? 0 : j;
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < GPX_MAX_DIM; ++i)
+        if (i < kp.d) kacc_dim<FAM>(acc, kp, i, X[i * ldx + jx], Y[i * ldy + jy]);
+    out[j] = kfinish<FAM>(acc, kp);
+}
+
+extern "C" int gpx_kernel_pairwise(gpx_handle h, const double* X, int64_t nx, int64_t ldx, const double* Y, int64_t ny,
+                                   int64_t ldy, double* out, void* stream) {
+    GPX_NEED_KERNEL(h);
+    GPX_REQUIRE(nx >= 0 && ny >= 0, GPX_EINVAL, "negative size");
+    GPX_REQUIRE(nx == ny || nx == 1 || ny == 1, GPX_EINVAL,
+                "point counts must match or one side must be a single point (kernels.py:58-63)");
+    const int64_t n = nx > ny ? nx : ny;
+    if (n == 0 || nx == 0 || ny == 0) return GPX_OK;
+    GPX_REQUIRE(X && Y && out, GPX_EINVAL, "NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    GPX_DISPATCH_FAMILY(h->kp.family, (pairwise_kernel<FAM><<<grid, 256, 0, st>>>(h->kp, X, nx, ldx, Y, ny, ldy, out, n)));
+    return gpx_check_launch("gpx_kernel_pairwise");
+}
+
+extern "C" int gpx_prior_diag(gpx_handle h, const double* X, int64_t n, int64_t ldx, double* out, void* stream) {
+    return gpx_kernel_pairwise(h, X, n, ldx, X, n, ldx, out, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1  Gram block.  One thread owns one column j (its coordinates stay in registers), a block walks
+// GRAM_ROWS rows whose coordinates sit in shared memory (broadcast reads); stores are coalesced in j.
+// Algorithmic traffic: 8 B written per element (+ 8 d (nx+ny) read).
+// ---------------------------------------------------------------------------------------------
+#define GRAM_ROWS 16
+
+template <int FAM>
+__global__ void __launch_bounds__(256) gram_kernel(const __grid_constant__ KParams kp, const double* __restrict__ X,
+                                                    int64_t nx, int64_t ldx, const double* __restrict__ Y, int64_t ny,
+                                                    int64_t ldy, double* __restrict__ out, int64_t ld, int add_diag,
+                                                    const double* __restrict__ nugvec, double nug) {
+    __shared__ double sx[GPX_MAX_DIM][GRAM_ROWS];
+    const int d = kp.d;
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    double y[GPX_MAX_DIM];
+#pragma unroll
+    for (int i = 0; i < GPX_MAX_DIM; ++i) y[i] = (i < d && j < ny) ? Y[i * ldy + j] : 0.0;
+
+    for (int64_t i0 = (int64_t)blockIdx.y * GRAM_ROWS; i0 < nx; i0 += (int64_t)gridDim.y * GRAM_ROWS) {
+        __syncthreads();
+        if (threadIdx.x < GRAM_ROWS * d) {
+            const int i = threadIdx.x / GRAM_ROWS, r = threadIdx.x % GRAM_ROWS;
+            sx[i][r] = (i0 + r < nx) ? X[i * ldx + i0 + r] : 0.0;
+        }
+        __syncthreads();
+        if (j < ny) {
+#pragma unroll 4
+            for (int r = 0; r < GRAM_ROWS; ++r) {
+                const int64_t row = i0 + r;
+                if (row >= nx) break;
+                double acc = 0.0;
+#pragma unroll
+                for (int i = 0; i < GPX_MAX_DIM; ++i)
+                    if (i < d) kacc_dim<FAM>(acc, kp, i, sx[i][r], y[i]);
+                double v = kfinish<FAM>(acc, kp);
+                if (add_diag && row == j) v += nugvec ? nugvec[row] : nug;
+                __stcs(out + row * ld + j, v);
+            }
+        }
+    }
+}
+
+extern "C" int gpx_gram(gpx_handle h, const double* X, int64_t nx, int64_t ldx, const double* Y, int64_t ny, int64_t ldy,
+                        double* out, int64_t ld, int add_diag, const double* nugget_vec, double nugget, void* stream) {
+    GPX_NEED_KERNEL(h);
+    GPX_REQUIRE(nx >= 0 && ny >= 0 && ld >= ny, GPX_EINVAL, "bad sizes");
+    if (nx == 0 || ny == 0) return GPX_OK;
+    GPX_REQUIRE(X && Y && out, GPX_EINVAL, "NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t gy = (nx + GRAM_ROWS - 1) / GRAM_ROWS;
+    if (gy > 32768) gy = 32768;
+    dim3 grid((unsigned)((ny + 255) / 256), (unsigned)gy);
+    GPX_DISPATCH_FAMILY(h->kp.family, (gram_kernel<FAM><<<grid, 256, 0, st>>>(h->kp, X, nx, ldx, Y, ny, ldy, out, ld,
+                                                                           add_diag, nugget_vec, nugget)));
+    return gpx_check_launch("gpx_gram");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Prepared side for the tensor-core Gram prologue.
+//   SE      e = -1/2 sum a (x-y)^2      = [-1/2 sum a x^2] + [-1/2 sum a y^2] + sum (a x) y
+//   MATERN  q = sum (x-y)^2             = [sum x^2] + [sum y^2] + sum (-2 x) y
+//   MEHLER  e = -sum c (a x^2 - b x y + a y^2) = [-sum c a x^2] + [-sum c a y^2] + sum (c b x) y
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prep_side_kernel(const __grid_constant__ KParams kp, int side,
+                                                         const double* __restrict__ X, int64_t n, int64_t ldx,
+                                                         double* __restrict__ rows, double* __restrict__ scal, int64_t ld) {
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= ld) return;
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < GPX_KROWS; ++i) {
+        double r = 0.0;
+        if (i < kp.d && j < n) {
+            const double x = X[i * ldx + j];
+            if (kp.family == GPX_SE) {
+                s = fma(x * x, kp.a[i], s);
+                r = side == GPX_SIDE_A ? x * kp.a[i] : x;
+            } else if (kp.family == GPX_MATERN32) {
+                s = fma(x, x, s);
+                r = side == GPX_SIDE_A ? -2.0 * x : x;
+            } else {
+                s = fma(x * x, kp.c[i] * kp.a[i], s);
+                r = side == GPX_SIDE_A ? kp.c[i] * kp.b[i] * x : x;
+            }
+        }
+        rows[i * ld + j] = r;
+    }
+    if (kp.family == GPX_SE) s *= -0.5;
+    if (kp.family == GPX_MEHLER) s = -s;
+    scal[j] = j < n ? s : 0.0;
+}
+
+extern "C" int gpx_prep_side(gpx_handle h, int side, const double* X, int64_t n, int64_t ldx, double* rows, double* scal,
+                             int64_t ld, void* stream) {
+    GPX_NEED_KERNEL(h);
+    GPX_REQUIRE(side == GPX_SIDE_A || side == GPX_SIDE_B, GPX_EINVAL, "bad side");
+    GPX_REQUIRE(n >= 0 && ld >= n, GPX_EINVAL, "bad sizes");
+    if (ld == 0) return GPX_OK;
+    GPX_REQUIRE(rows && scal && (X || n == 0), GPX_EINVAL, "NULL pointer");
+    prep_side_kernel<<<(unsigned)((ld + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->kp, side, X, n, ldx, rows, scal, ld);
+    return gpx_check_launch("gpx_prep_side");
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7  arg-reduce and deterministic sum: per-block partials + last-block-done finish (one launch).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) argreduce_kernel(const double* __restrict__ v, const double* __restrict__ w,
+                                                         const uint8_t* __restrict__ mask, int64_t n, int minimize,
+                                                         double* red_val, int64_t* red_idx, unsigned int* counter,
+                                                         double* best, int64_t* idx) {
+    __shared__ double sv[8];
+    __shared__ int64_t si[8];
+    __shared__ bool last;
+    const bool mn = minimize != 0;
+    double bv = 0.0;
+    int64_t bi = -1;
+    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < n; j += (int64_t)gridDim.x * 256) {
+        if (mask && mask[j]) continue;
+        const double s = w ? v[j] * w[j] : v[j];
+        if (gpx_better(s, j, bv, bi, mn)) {
+            bv = s;
+            bi = j;
+        }
+    }
+    gpx_warp_argreduce(bv, bi, mn);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        sv[warp] = bv;
+        si[warp] = bi;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        bv = lane < 8 ? sv[lane] : 0.0;
+        bi = lane < 8 ? si[lane] : -1;
+        gpx_warp_argreduce(bv, bi, mn);
+        if (lane == 0) {
+            red_val[blockIdx.x] = bv;
+            red_idx[blockIdx.x] = bi;
+            __threadfence();
+            const unsigned int t = atomicAdd(counter, 1u);
+            last = (t == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    bv = 0.0;
+    bi = -1;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += 256) {
+        const double ov = __ldcg(red_val + b);
+        const int64_t oi = __ldcg(red_idx + b);
+        if (gpx_better(ov, oi, bv, bi, mn)) {
+            bv = ov;
+            bi = oi;
+        }
+    }
+    gpx_warp_argreduce(bv, bi, mn);
+    if (lane == 0) {
+        sv[warp] = bv;
+        si[warp] = bi;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        bv = lane < 8 ? sv[lane] : 0.0;
+        bi = lane < 8 ? si[lane] : -1;
+        gpx_warp_argreduce(bv, bi, mn);
+        if (lane == 0) {
+            best[0] = bv;
+            idx[0] = bi;
+            *counter = 0u;
+        }
+    }
+}
+
+int gpx_argreduce_impl(gpx_handle h, const double* v, const double* weights, const uint8_t* mask, int64_t n,
+                       int minimize, double* best, int64_t* idx, cudaStream_t st) {
+    int64_t blocks = (n + 1023) / 1024;
+    if (blocks < 1) blocks = 1;
+    if (blocks > GPX_RED_SLOTS) blocks = GPX_RED_SLOTS;
+    argreduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(v, weights, mask, n, minimize, h->red_val, h->red_idx,
+                                                      h->red_counter, best, idx);
+    return gpx_check_launch("gpx_argreduce");
+}
+
+extern "C" int gpx_argreduce(gpx_handle h, const double* v, const double* weights, const uint8_t* mask, int64_t n,
+                             int minimize, double* best, int64_t* idx, void* stream) {
+    GPX_REQUIRE(h != nullptr, GPX_EINVAL, "handle is NULL");
+    GPX_REQUIRE(n >= 0 && best && idx && (v || n == 0), GPX_EINVAL, "bad arguments");
+    return gpx_argreduce_impl(h, v, weights, mask, n, minimize, best, idx, (cudaStream_t)stream);
+}
+
+__device__ __forceinline__ double gpx_block_sum(double s, double* sm) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sm[warp] = s;
+    __syncthreads();
+    double t = 0.0;
+    if (warp == 0) {
+        t = lane < 8 ? sm[lane] : 0.0;
+#pragma unroll
+        for (int off = 4; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+    }
+    return t;  // valid in warp 0
+}
+
+__global__ void __launch_bounds__(256) sum_kernel(const double* __restrict__ v, int64_t n, double* red_val,
+                                                   unsigned int* counter, double* out) {
+    __shared__ double sm[8];
+    __shared__ bool last;
+    double s = 0.0;
+    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < n; j += (int64_t)gridDim.x * 256) s += v[j];
+    s = gpx_block_sum(s, sm);
+    if (threadIdx.x == 0) {
+        red_val[blockIdx.x] = s;
+        __threadfence();
+        last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    s = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += 256) s += __ldcg(red_val + b);
+    s = gpx_block_sum(s, sm);
+    if (threadIdx.x == 0) {
+        out[0] = s;
+        *counter = 0u;
+    }
+}
+
+int gpx_sum_impl(gpx_handle h, const double* v, int64_t n, double* out, cudaStream_t st) {
+    int64_t blocks = (n + 4095) / 4096;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 1024) blocks = 1024;
+    // slots [1024, 2048) of the scratch and ticket 1, so that a sum can sit next to an arg-reduce
+    sum_kernel<<<(unsigned)blocks, 256, 0, st>>>(v, n, h->red_val + 1024, h->red_counter + 1, out);
+    return gpx_check_launch("gpx_sum");
+}
+
+extern "C" int gpx_sum(gpx_handle h, const double* v, int64_t n, double* out, void* stream) {
+    GPX_REQUIRE(h != nullptr && out && n >= 0 && (v || n == 0), GPX_EINVAL, "bad arguments");
+    return gpx_sum_impl(h, v, n, out, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3+K4 incremental row append.  Two adjacent columns per thread (16-byte streaming loads), the pivot's
+// W-column in shared memory, 8 independent loads in flight per thread.  Reads 8*n*ncols bytes.
+// ---------------------------------------------------------------------------------------------
+template <int FAM, int SRC>
+__global__ void __launch_bounds__(128) append_row_kernel(const __grid_constant__ KParams kp, const double* __restrict__ rec,
+                                                          const double* __restrict__ src_row, const double* __restrict__ Y,
+                                                          int64_t ncols, int64_t ldy, double* __restrict__ W, int64_t ldw,
+                                                          int n, double* __restrict__ var) {
+    extern __shared__ double sl[];
+    for (int i = threadIdx.x; i < n; i += 128) sl[i] = rec[GPX_PIVOT_HDR + i];
+    __syncthreads();
+    const int64_t j = ((int64_t)blockIdx.x * 128 + threadIdx.x) * 2;
+    if (j >= ncols) return;
+    const double* wp = W + j;
+    double a0 = 0.0, a1 = 0.0;
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+        double2 w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = __ldcs(reinterpret_cast<const double2*>(wp + (int64_t)(i + u) * ldw));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(sl[i + u], w[u].x, a0);
+            a1 = fma(sl[i + u], w[u].y, a1);
+        }
+    }
+    for (; i < n; ++i) {
+        const double2 w = __ldcs(reinterpret_cast<const double2*>(wp + (int64_t)i * ldw));
+        a0 = fma(sl[i], w.x, a0);
+        a1 = fma(sl[i], w.y, a1);
+    }
+    double s0, s1;
+    if (SRC == GPX_ROW_KERNEL) {
+        double k0 = 0.0, k1 = 0.0;
+#pragma unroll
+        for (int q = 0; q < GPX_MAX_DIM; ++q)
+            if (q < kp.d) {
+                const double xp = rec[3 + q];
+                const double2 y = *reinterpret_cast<const double2*>(Y + q * ldy + j);
+                kacc_dim<FAM>(k0, kp, q, xp, y.x);
+                kacc_dim<FAM>(k1, kp, q, xp, y.y);
+            }
+        s0 = kfinish<FAM>(k0, kp);
+        s1 = kfinish<FAM>(k1, kp);
+    } else {
+        const double2 s = *reinterpret_cast<const double2*>(src_row + j);
+        s0 = s.x;
+        s1 = s.y;
+    }
+    const double lnn = sqrt(rec[2]);
+    const double w0 = (s0 - a0) / lnn;
+    const double w1 = (s1 - a1) / lnn;
+    const bool two = j + 1 < ncols;
+    double* dst = W + (int64_t)n * ldw + j;
+    dst[0] = w0;
+    dst[1] = two ? w1 : 0.0;
+    var[j] -= w0 * w0;
+    if (two) var[j + 1] -= w1 * w1;
+}
+
+extern "C" int gpx_append_row(gpx_handle h, int row_source, const double* rec, const double* src_row, const double* Y,
+                              int64_t ncols, int64_t ldy, double* W, int64_t ldw, int64_t n, double* var, void* stream) {
+    GPX_NEED_KERNEL(h);
+    GPX_REQUIRE(row_source == GPX_ROW_KERNEL || row_source == GPX_ROW_MATRIX, GPX_EINVAL, "bad row source");
+    GPX_REQUIRE(ncols >= 0 && n >= 0, GPX_EINVAL, "negative size");
+    if (ncols == 0) return GPX_OK;
+    GPX_REQUIRE(rec && W && var, GPX_EINVAL, "NULL pointer");
+    GPX_REQUIRE((ldw % 2) == 0 && ldw >= ncols + (ncols & 1), GPX_EALIGN, "ldw must be even and cover an even column count");
+    GPX_REQUIRE(gpx_aligned16(W), GPX_EALIGN, "W must be 16-byte aligned");
+    if (row_source == GPX_ROW_KERNEL) {
+        GPX_REQUIRE(Y != nullptr, GPX_EINVAL, "Y is NULL");
+        GPX_REQUIRE((ldy % 2) == 0 && ldy >= ncols + (ncols & 1) && gpx_aligned16(Y), GPX_EALIGN,
+                    "Y must be 16-byte aligned with an even leading dimension");
+    } else {
+        GPX_REQUIRE(src_row != nullptr && gpx_aligned16(src_row), GPX_EALIGN, "src_row must be 16-byte aligned");
+    }
+    const size_t smem = (size_t)n * sizeof(double);
+    GPX_REQUIRE(smem <= 200 * 1024, GPX_ESIZE, "design size exceeds the shared-memory column buffer (25600)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((ncols + 255) / 256);
+#define GPX_APPEND_LAUNCH(F, S)                                                                                      \
+    do {                                                                                                             \
+        if (smem > 48 * 1024)                                                                                        \
+            cudaFuncSetAttribute(append_row_kernel<F, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   \
+        append_row_kernel<F, S><<<grid, 128, smem, st>>>(h->kp, rec, src_row, Y, ncols, ldy, W, ldw, (int)n, var);    \
+    } while (0)
+    if (row_source == GPX_ROW_KERNEL) {
+        GPX_DISPATCH_FAMILY(h->kp.family, GPX_APPEND_LAUNCH(FAM, GPX_ROW_KERNEL));
+    } else {
+        GPX_APPEND_LAUNCH(GPX_SE, GPX_ROW_MATRIX);
+    }
+#undef GPX_APPEND_LAUNCH
+    return gpx_check_launch("gpx_append_row");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pivot bookkeeping (single small blocks; latency only)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_pivot_kernel(const double* __restrict__ W, int64_t ldw, int n,
+                                                            const double* __restrict__ var, const double* __restrict__ X,
+                                                            int64_t ldx, int d, const double* __restrict__ score,
+                                                            const int64_t* __restrict__ idx, int64_t offset, double noise,
+                                                            double* __restrict__ rec) {
+    const int64_t p = idx[0];
+    if (p < 0) {
+        if (threadIdx.x == 0 && blockIdx.x == 0) {
+            rec[0] = score ? score[0] : 0.0;
+            rec[1] = -1.0;
+            rec[2] = 1.0;
+        }
+        return;
+    }
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            rec[0] = score ? score[0] : 0.0;
+            rec[1] = (double)(p + offset);
+            rec[2] = var[p] + noise;
+        }
+        if (threadIdx.x < GPX_MAX_DIM) rec[3 + threadIdx.x] = threadIdx.x < d ? X[threadIdx.x * ldx + p] : 0.0;
+    }
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) rec[GPX_PIVOT_HDR + i] = W[(int64_t)i * ldw + p];
+}
+
+extern "C" int gpx_gather_pivot(gpx_handle h, const double* W, int64_t ldw, int64_t n, const double* var, const double* X,
+                                int64_t ldx, const double* score_dev, const int64_t* idx_dev, int64_t index_offset,
+                                double noise, double* rec, void* stream) {
+    GPX_NEED_KERNEL(h);
+    GPX_REQUIRE(n >= 0 && var && X && idx_dev && rec && (W || n == 0), GPX_EINVAL, "bad arguments");
+    unsigned grid = (unsigned)((n + 255) / 256);
+    if (grid < 1) grid = 1;
+    if (grid > 64) grid = 64;
+    gather_pivot_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, ldw, (int)n, var, X, ldx, h->kp.d, score_dev, idx_dev,
+                                                              index_offset, noise, rec);
+    return gpx_check_launch("gpx_gather_pivot");
+}
+
+__global__ void __launch_bounds__(256) select_pivot_kernel(const double* __restrict__ recs, int nrec, int64_t stride, int n,
+                                                            int minimize, double* __restrict__ out) {
+    __shared__ int win;
+    if (threadIdx.x == 0) {
+        double bv = 0.0;
+        int64_t bi = -1;
+        int bw = 0;
+        for (int r = 0; r < nrec; ++r) {
+            const double v = recs[r * stride];
+            const int64_t i = (int64_t)recs[r * stride + 1];
+            if (gpx_better(v, i, bv, bi, minimize != 0)) {
+                bv = v;
+                bi = i;
+                bw = r;
+            }
+        }
+        win = bw;
+    }
+    __syncthreads();
+    const double* src = recs + (int64_t)win * stride;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < GPX_PIVOT_HDR + n; i += gridDim.x * 256) out[i] = src[i];
+}
+
+extern "C" int gpx_select_pivot(gpx_handle h, const double* recs, int nrec, int64_t stride, int64_t n, int minimize,
+                                double* rec_out, void* stream) {
+    GPX_REQUIRE(h && recs && rec_out && nrec >= 1 && n >= 0 && stride >= GPX_PIVOT_HDR + n, GPX_EINVAL, "bad arguments");
+    unsigned grid = (unsigned)((GPX_PIVOT_HDR + n + 255) / 256);
+    if (grid > 64) grid = 64;
+    select_pivot_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(recs, nrec, stride, (int)n, minimize, rec_out);
+    return gpx_check_launch("gpx_select_pivot");
+}
+
+__global__ void __launch_bounds__(256) store_pivot_kernel(const double* __restrict__ rec, int n, double* U, int64_t ldu,
+                                                           int64_t* picks, double* scores) {
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
+        if (U) U[(int64_t)i * ldu + n] = rec[GPX_PIVOT_HDR + i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (U) U[(int64_t)n * ldu + n] = sqrt(rec[2]);
+        if (picks) picks[n] = (int64_t)rec[1];
+        if (scores) scores[n] = rec[0];
+    }
+}
+
+extern "C" int gpx_store_pivot(gpx_handle h, const double* rec, int64_t n, double* U, int64_t ldu, int64_t* picks,
+                               double* scores, void* stream) {
+    GPX_REQUIRE(h && rec && n >= 0, GPX_EINVAL, "bad arguments");
+    unsigned grid = (unsigned)((n + 255) / 256);
+    if (grid < 1) grid = 1;
+    if (grid > 64) grid = 64;
+    store_pivot_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rec, (int)n, U, ldu, picks, scores);
+    return gpx_check_launch("gpx_store_pivot");
+}
+
+__global__ void set_mask_kernel(uint8_t* mask, const int64_t* idx, uint8_t value) {
+    if (idx[0] >= 0) mask[idx[0]] = value;
+}
+
+extern "C" int gpx_set_mask(gpx_handle h, uint8_t* mask, const int64_t* idx_dev, uint8_t value, void* stream) {
+    GPX_REQUIRE(h && mask && idx_dev, GPX_EINVAL, "bad arguments");
+    set_mask_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(mask, idx_dev, value);
+    return gpx_check_launch("gpx_set_mask");
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4  column sums of squares (posterior variance from a materialised W)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) colsumsq_kernel(const double* __restrict__ W, int64_t n, int64_t ncols, int64_t ldw,
+                                                        const double* __restrict__ base, double* __restrict__ out) {
+    const int64_t j = ((int64_t)blockIdx.x * 128 + threadIdx.x) * 2;
+    if (j >= ncols) return;
+    double a0 = 0.0, a1 = 0.0;
+    int64_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        double2 w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) w[u] = *reinterpret_cast<const double2*>(W + (i + u) * ldw + j);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            a0 = fma(w[u].x, w[u].x, a0);
+            a1 = fma(w[u].y, w[u].y, a1);
+        }
+    }
+    for (; i < n; ++i) {
+        const double2 w = *reinterpret_cast<const double2*>(W + i * ldw + j);
+        a0 = fma(w.x, w.x, a0);
+        a1 = fma(w.y, w.y, a1);
+    }
+    out[j] = base ? base[j] - a0 : a0;
+    if (j + 1 < ncols) out[j + 1] = base ? base[j + 1] - a1 : a1;
+}
+
+extern "C" int gpx_colsumsq(gpx_handle h, const double* W, int64_t n, int64_t ncols, int64_t ldw, const double* base,
+                            double* out, void* stream) {
+    GPX_REQUIRE(h && out && n >= 0 && ncols >= 0, GPX_EINVAL, "bad arguments");
+    if (ncols == 0) return GPX_OK;
+    GPX_REQUIRE(W || n == 0, GPX_EINVAL, "W is NULL");
+    GPX_REQUIRE(n == 0 || ((ldw % 2) == 0 && ldw >= ncols + (ncols & 1) && gpx_aligned16(W)), GPX_EALIGN,
+                "W must be 16-byte aligned with an even leading dimension");
+    colsumsq_kernel<<<(unsigned)((ncols + 255) / 256), 128, 0, (cudaStream_t)stream>>>(W, n, ncols, ldw, base, out);
+    return gpx_check_launch("gpx_colsumsq");
+}
+
+// ---------------------------------------------------------------------------------------------
+// transpose (row-major points (n,d) <-> dimension-major (d,ld), and U <-> U^T)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ in, int64_t rows, int64_t cols,
+                                                         int64_t ld_in, double* __restrict__ out, int64_t ld_out) {
+    __shared__ double tile[32][33];
+    const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8)
+        if (r0 + r < rows && c0 + tx < cols) tile[r][tx] = in[(r0 + r) * ld_in + c0 + tx];
+    __syncthreads();
+    for (int c = ty; c < 32; c += 8)
+        if (c0 + c < cols && r0 + tx < rows) out[(c0 + c) * ld_out + r0 + tx] = tile[tx][c];
+}
+
+extern "C" int gpx_transpose(gpx_handle h, const double* in, int64_t rows, int64_t cols, int64_t ld_in, double* out,
+                             int64_t ld_out, void* stream) {
+    GPX_REQUIRE(h && rows >= 0 && cols >= 0, GPX_EINVAL, "bad arguments");
+    if (rows == 0 || cols == 0) return GPX_OK;
+    GPX_REQUIRE(in && out && ld_in >= cols && ld_out >= rows, GPX_EINVAL, "bad arguments");
+    const int64_t gy = (rows + 31) / 32;
+    GPX_REQUIRE(gy <= 65535 || true, GPX_ESIZE, "");
+    if (gy <= 65535) {
+        dim3 grid((unsigned)((cols + 31) / 32), (unsigned)gy);
+        transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, rows, cols, ld_in, out, ld_out);
+    } else {
+        // tall input (points (n,d) with huge n): walk the rows in slabs
+        const int64_t slab = 65535LL * 32;
+        for (int64_t r0 = 0; r0 < rows; r0 += slab) {
+            const int64_t rr = rows - r0 < slab ? rows - r0 : slab;
+            dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rr + 31) / 32));
+            transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in + r0 * ld_in, rr, cols, ld_in, out + r0, ld_out);
+        }
+    }
+    return gpx_check_launch("gpx_transpose");
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6  mutual-information helpers
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) score_mi_kernel(const double* __restrict__ num, const double* __restrict__ pd,
+                                                        double noise, const uint8_t* __restrict__ mask, int64_t n,
+                                                        double* __restrict__ score) {
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= n) return;
+    if (mask && mask[j]) {
+        score[j] = -INFINITY;
+        return;
+    }
+    const double den = 1.0 / pd[j] - noise;  // var(y | V minus A minus y)   experimentalDesign.py:277-281
+    score[j] = num[j] / den;                 // :284
+}
+
+extern "C" int gpx_score_mi(gpx_handle h, const double* num_var, const double* prec_diag, double noise,
+                            const uint8_t* mask, int64_t n, double* score_out, double* best, int64_t* idx, void* stream) {
+    GPX_REQUIRE(h && num_var && prec_diag && score_out && best && idx && n >= 1, GPX_EINVAL, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    score_mi_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(num_var, prec_diag, noise, mask, n, score_out);
+    int rc = gpx_check_launch("gpx_score_mi");
+    if (rc) return rc;
+    return gpx_argreduce_impl(h, score_out, nullptr, mask, n, 0, best, idx, st);
+}
+
+// out[i] = sum_{k >= max(i,p)} Y[k,i] * Y[k,p]   (Y lower triangular, row-major)
+__global__ void __launch_bounds__(128) mi_prec_column_kernel(const double* __restrict__ Y, int64_t n, int64_t ldy,
+                                                              const int64_t* __restrict__ pdev, double* __restrict__ out) {
+    const int64_t p = pdev[0];
+    const int64_t i = ((int64_t)blockIdx.x * 128 + threadIdx.x) * 2;
+    if (i >= n || p < 0) return;
+    // both columns i, i+1 start at k = max(i,p) (Y[i, i+1] = 0 is stored explicitly)
+    int64_t k = i > p ? i : p;
+    double a0 = 0.0, a1 = 0.0;
+    for (; k + 4 <= n; k += 4) {
+        double2 y[4];
+        double yp[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            y[u] = *reinterpret_cast<const double2*>(Y + (k + u) * ldy + i);
+            yp[u] = __ldg(Y + (k + u) * ldy + p);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            a0 = fma(y[u].x, yp[u], a0);
+            a1 = fma(y[u].y, yp[u], a1);
+        }
+    }
+    for (; k < n; ++k) {
+        const double2 y = *reinterpret_cast<const double2*>(Y + k * ldy + i);
+        const double yp = __ldg(Y + k * ldy + p);
+        a0 = fma(y.x, yp, a0);
+        a1 = fma(y.y, yp, a1);
+    }
+    out[i] = a0;
+    if (i + 1 < n) out[i + 1] = a1;
+}
+
+extern "C" int gpx_mi_prec_column(gpx_handle h, const double* Y, int64_t n, int64_t ldy, const int64_t* p_dev, double* out,
+                                  void* stream) {
+    GPX_REQUIRE(h && Y && p_dev && out && n >= 1, GPX_EINVAL, "bad arguments");
+    GPX_REQUIRE((ldy % 2) == 0 && ldy >= n + (n & 1) && gpx_aligned16(Y), GPX_EALIGN,
+                "Y must be 16-byte aligned with an even leading dimension");
+    mi_prec_column_kernel<<<(unsigned)((n + 255) / 256), 128, 0, (cudaStream_t)stream>>>(Y, n, ldy, p_dev, out);
+    return gpx_check_launch("gpx_mi_prec_column");
+}

@@ -1,0 +1,366 @@
+// K2 / K3: blocked FP64 Cholesky (A = U^T U, upper, row-major), triangular solves and the rank-1 append.
+//
+// potrf, right-looking in 128-wide block columns:
+//   (1) diagonal block: one CTA, block in shared memory, 32x32 sub-panels factored by ONE WARP with
+//       register-resident columns and shuffle broadcasts (the latency-critical part), the in-block panel
+//       solve and rank-32 update by the whole CTA;
+//   (2) block row  U12 = U11^-T A12   : one thread per column, forward substitution, U11 in shared memory;
+//   (3) trailing   A22 -= U12^T U12   : DMMA core (gpx_dgemm_tn_sub, upper tiles only).
+// trsm (W = U^-T B), left-looking in 128-row blocks: DMMA core (K = rows already solved) + the same
+// forward-substitution kernel.  With the Gram prologue the right-hand side K(D,Y) is never materialised.
+#include <math.h>
+
+#include "gpx_common.cuh"
+
+namespace {
+
+constexpr int NB = 128;          // block size
+constexpr int SLD = NB + 1;      // padded shared-memory stride
+
+// ---- 32x32 upper Cholesky by one warp: lane j owns column j of the symmetric block ---------------
+// On exit col[i] (i <= j) = U[i][j].  Returns 0 or 1 + local index of the first non-positive pivot.
+__device__ __forceinline__ int warp_potf2_32(double (&col)[32], int lane) {
+    int bad = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const double akk = __shfl_sync(0xffffffffu, col[k], k);
+        if (!(akk > 0.0) && bad == 0) bad = k + 1;
+        const double dkk = sqrt(akk);
+        if (lane == k) col[k] = dkk;
+        if (lane > k) col[k] = col[k] / dkk;  // U[k][lane]
+#pragma unroll
+        for (int i = k + 1; i < 32; ++i) {
+            const double uki = __shfl_sync(0xffffffffu, col[k], i);  // U[k][i]
+            if (lane >= i) col[i] = fma(-uki, col[k], col[i]);
+        }
+    }
+    return bad;
+}
+
+// ---- diagonal block factorisation -----------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, int64_t ld, int b, int64_t kb, int* info) {
+    extern __shared__ double S[];  // NB x SLD, upper part meaningful
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // load (identity padding beyond b so that ragged blocks factor cleanly)
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e / NB, c = e % NB;
+        double v = (r == c) ? 1.0 : 0.0;
+        if (r < b && c < b && c >= r) v = A[(kb + r) * ld + kb + c];
+        S[r * SLD + c] = v;
+    }
+    __syncthreads();
+    for (int p = 0; p < NB; p += 32) {
+        if (p >= b) break;
+        if (warp == 0) {
+            double col[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) col[i] = S[(p + i) * SLD + p + lane];
+            const int bad = warp_potf2_32(col, lane);
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (i <= lane) S[(p + i) * SLD + p + lane] = col[i];
+            if (lane == 0 && bad && p + bad <= b) atomicCAS(info, 0, (int)(kb + p + bad));
+        }
+        __syncthreads();
+        const int rest = NB - (p + 32);
+        if (rest > 0) {
+            // in-block panel solve: rows p..p+32, columns p+32..NB : one thread per column
+            if (tid < rest) {
+                const int c = p + 32 + tid;
+                double x[32];
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    double v = S[(p + r) * SLD + c];
+#pragma unroll
+                    for (int s = 0; s < r; ++s) v = fma(-S[(p + s) * SLD + p + r], x[s], v);
+                    x[r] = v / S[(p + r) * SLD + p + r];
+                }
+#pragma unroll
+                for (int r = 0; r < 32; ++r) S[(p + r) * SLD + c] = x[r];
+            }
+            __syncthreads();
+            // rank-32 update of the trailing upper part of the block
+            for (int e = tid; e < rest * rest; e += 256) {
+                const int i = p + 32 + e / rest, j = p + 32 + e % rest;
+                if (j < i) continue;
+                double v = S[i * SLD + j];
+#pragma unroll 8
+                for (int s = 0; s < 32; ++s) v = fma(-S[(p + s) * SLD + i], S[(p + s) * SLD + j], v);
+                S[i * SLD + j] = v;
+            }
+            __syncthreads();
+        }
+    }
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e / NB, c = e % NB;
+        if (r < b && c < b && c >= r) A[(kb + r) * ld + kb + c] = S[r * SLD + c];
+    }
+}
+
+// ---- forward substitution  X = T^-T B  for a b x b upper-triangular T (b <= 128), in place --------
+// One thread per column; 32 solution entries live in registers at a time, earlier ones are re-read.
+// TRANS_T == false : T[s][r] = Tm[s*ldt + r]   (U stored upper, row-major)             -> X = U^-T B
+// TRANS_T == true  : T[s][r] = Tm[r*ldt + s], rows walked bottom-up                    -> X = L^-T B = U^-1 B (L = U^T)
+template <bool BACK>
+__global__ void __launch_bounds__(128) tri_solve_kernel(const double* __restrict__ Tm, int64_t ldt, int b,
+                                                         double* __restrict__ B, int64_t ldb, int64_t ncols) {
+    extern __shared__ double St[];  // b x SLD : St[s*SLD + r] = coefficient multiplying x_s in equation r
+    for (int e = threadIdx.x; e < b * b; e += 128) {
+        const int s = e / b, r = e % b;
+        // forward:  eq r: sum_{s<=r} U[s][r] x_s = rhs_r.   backward (rows reversed): eq r': sum_{s'<=r'} L[..]..
+        double v;
+        if (!BACK) {
+            v = (s <= r) ? Tm[(int64_t)s * ldt + r] : 0.0;
+        } else {
+            // reversed indices: s' = b-1-s, r' = b-1-r ; U[r'][s'] with s' >= r'  <=>  s <= r ; L = U^T given: Tm[s'*ldt + r']
+            const int sp = b - 1 - s, rp = b - 1 - r;
+            v = (s <= r) ? Tm[(int64_t)sp * ldt + rp] : 0.0;
+        }
+        St[s * SLD + r] = v;
+    }
+    __syncthreads();
+    const int64_t j = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (j >= ncols) return;
+    auto rowptr = [&](int r) -> double* { return B + (int64_t)(BACK ? (b - 1 - r) : r) * ldb + j; };
+    for (int rb = 0; rb < b; rb += 32) {
+        double x[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) x[r] = (rb + r < b) ? *rowptr(rb + r) : 0.0;
+        for (int s = 0; s < rb; ++s) {
+            const double xs = *rowptr(s);
+            const double* ts = St + s * SLD + rb;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) x[r] = fma(-ts[r], xs, x[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            if (rb + r < b) {
+                double v = x[r];
+#pragma unroll
+                for (int s = 0; s < r; ++s) v = fma(-St[(rb + s) * SLD + rb + r], x[s], v);
+                x[r] = v / St[(rb + r) * SLD + rb + r];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+            if (rb + r < b) *rowptr(rb + r) = x[r];
+    }
+}
+
+template <bool BACK>
+int launch_tri_solve(const double* Tm, int64_t ldt, int b, double* B, int64_t ldb, int64_t ncols, cudaStream_t st) {
+    static bool configured = false;
+    const size_t smem = (size_t)NB * SLD * sizeof(double);
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tri_solve_kernel<BACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            gpx_set_error("tri_solve: shared memory opt-in failed: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        configured = true;
+    }
+    if (ncols <= 0 || b <= 0) return GPX_OK;
+    tri_solve_kernel<BACK><<<(unsigned)((ncols + 127) / 128), 128, (size_t)b * SLD * sizeof(double), st>>>(Tm, ldt, b, B, ldb, ncols);
+    return gpx_check_launch("tri_solve");
+}
+
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+
+}  // namespace
+
+extern "C" int gpx_potrf(gpx_handle h, double* A, int64_t n, int64_t ld, int* info, void* stream) {
+    GPX_REQUIRE(h && info && n >= 0, GPX_EINVAL, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    set_int_kernel<<<1, 1, 0, st>>>(info, 0);
+    if (n == 0) return gpx_check_launch("gpx_potrf");
+    GPX_REQUIRE(A && ld >= n, GPX_EINVAL, "bad matrix");
+    GPX_REQUIRE((ld % 2) == 0 && gpx_aligned16(A), GPX_EALIGN, "A must be 16-byte aligned with an even leading dimension");
+    static bool configured = false;
+    const size_t smem = (size_t)NB * SLD * sizeof(double);
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            gpx_set_error("gpx_potrf: shared memory opt-in failed: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        configured = true;
+    }
+    for (int64_t kb = 0; kb < n; kb += NB) {
+        const int b = (int)(n - kb < NB ? n - kb : NB);
+        potrf_diag_kernel<<<1, 256, smem, st>>>(A, ld, b, kb, info);
+        int rc = gpx_check_launch("gpx_potrf diag");
+        if (rc) return rc;
+        const int64_t rest = n - kb - b;
+        if (rest > 0) {
+            double* A12 = A + kb * ld + kb + b;
+            rc = launch_tri_solve<false>(A + kb * ld + kb, ld, b, A12, ld, rest, st);
+            if (rc) return rc;
+            rc = gpx_dgemm_tn_sub(h, A12, ld, A12, ld, A + (kb + b) * ld + kb + b, ld, rest, rest, b, 1, stream);
+            if (rc) return rc;
+        }
+    }
+    return GPX_OK;
+}
+
+extern "C" int gpx_trsm_gram(gpx_handle h, const double* U, int64_t n, int64_t ldu, const double* Da_rows,
+                             const double* Da_scal, int64_t ldd, const double* Y, const double* Yb_rows, const double* Yb_scal,
+                             int64_t ny, int64_t ldy, double* W, int64_t ldw, double* var_out, void* stream) {
+    GPX_NEED_KERNEL(h);
+    GPX_REQUIRE(n >= 0 && ny >= 0, GPX_EINVAL, "negative size");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (ny == 0) return GPX_OK;
+    if (n > 0) {
+        GPX_REQUIRE(U && Da_rows && Da_scal && Yb_rows && Yb_scal && W, GPX_EINVAL, "NULL pointer");
+        GPX_REQUIRE(ldd == ldu, GPX_EINVAL, "the prepared design side must share the leading dimension of U");
+        for (int64_t kb = 0; kb < n; kb += NB) {
+            const int b = (int)(n - kb < NB ? n - kb : NB);
+            // block row:  W[kb:kb+b, :] = K(D[kb:kb+b], Y) - U[0:kb, kb:kb+b]^T W[0:kb, :]
+            rc = gpx_launch_core_store(h, U + kb, ldu, Da_rows + kb, Da_scal + kb, b, W, ldw, Yb_rows, Yb_scal, ny, kb,
+                                       W + kb * ldw, ldw, st);
+            if (rc) return rc;
+            rc = launch_tri_solve<false>(U + kb * ldu + kb, ldu, b, W + kb * ldw, ldw, ny, st);
+            if (rc) return rc;
+        }
+    }
+    if (var_out) {
+        GPX_REQUIRE(Y != nullptr, GPX_EINVAL, "Y is required for the variance output");
+        rc = gpx_prior_diag(h, Y, ny, ldy, var_out, stream);
+        if (rc) return rc;
+        if (n > 0) rc = gpx_colsumsq(h, W, n, ny, ldw, var_out, var_out, stream);
+        if (rc) return rc;
+    }
+    return GPX_OK;
+}
+
+static int trsm_forward(gpx_handle h, const double* U, int64_t n, int64_t ldu, double* B, int64_t ncols, int64_t ldb,
+                        int lower_tri_rhs, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int64_t kb = 0; kb < n; kb += NB) {
+        const int b = (int)(n - kb < NB ? n - kb : NB);
+        int64_t active = ncols;
+        if (lower_tri_rhs && kb + b < active) active = kb + b;  // block row kb of U^-T is zero right of its diagonal block
+        int rc;
+        if (kb > 0) {
+            rc = gpx_dgemm_tn_sub(h, U + kb, ldu, B, ldb, B + kb * ldb, ldb, b, active, kb, 0, stream);
+            if (rc) return rc;
+        }
+        rc = launch_tri_solve<false>(U + kb * ldu + kb, ldu, b, B + kb * ldb, ldb, active, st);
+        if (rc) return rc;
+    }
+    return GPX_OK;
+}
+
+extern "C" int gpx_trsm(gpx_handle h, const double* U, int64_t n, int64_t ldu, double* B, int64_t ncols, int64_t ldb,
+                        void* stream) {
+    GPX_REQUIRE(h && n >= 0 && ncols >= 0, GPX_EINVAL, "bad arguments");
+    if (n == 0 || ncols == 0) return GPX_OK;
+    GPX_REQUIRE(U && B, GPX_EINVAL, "NULL pointer");
+    return trsm_forward(h, U, n, ldu, B, ncols, ldb, 0, stream);
+}
+
+// Y = U^-T as an explicit lower-triangular matrix (MI set-up: precision diagonal and columns come from it).
+__global__ void __launch_bounds__(256) set_identity_kernel(double* Y, int64_t n, int64_t ld) {
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= n * ld) return;
+    const int64_t r = e / ld, c = e % ld;
+    Y[e] = (r == c) ? 1.0 : 0.0;
+}
+
+extern "C" int gpx_trtri_t(gpx_handle h, const double* U, int64_t n, int64_t ldu, double* Y, int64_t ldy, void* stream) {
+    GPX_REQUIRE(h && n >= 0, GPX_EINVAL, "bad arguments");
+    if (n == 0) return GPX_OK;
+    GPX_REQUIRE(U && Y && ldy >= n, GPX_EINVAL, "bad arguments");
+    const int64_t total = n * ldy;
+    set_identity_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(Y, n, ldy);
+    int rc = gpx_check_launch("gpx_trtri_t identity");
+    if (rc) return rc;
+    return trsm_forward(h, U, n, ldu, Y, n, ldy, 1, stream);
+}
+
+extern "C" int gpx_trsm_back(gpx_handle h, const double* Ut, int64_t n, int64_t ldu, double* B, int64_t ncols, int64_t ldb,
+                             void* stream) {
+    GPX_REQUIRE(h && n >= 0 && ncols >= 0, GPX_EINVAL, "bad arguments");
+    if (n == 0 || ncols == 0) return GPX_OK;
+    GPX_REQUIRE(Ut && B, GPX_EINVAL, "NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    // bottom-up over block rows; Ut = U^T (lower, row-major) so that the update operand is K-major:
+    //   B[kb:kb+b, :] -= sum_{k >= kb+b} U[kb+i, k] B[k, :] = sum_k Ut[k*ldu + kb + i] B[k, :]
+    const int64_t nblk = (n + NB - 1) / NB;
+    for (int64_t blk = nblk - 1; blk >= 0; --blk) {
+        const int64_t kb = blk * NB;
+        const int b = (int)(n - kb < NB ? n - kb : NB);
+        const int64_t below = n - kb - b;
+        int rc;
+        if (below > 0) {
+            rc = gpx_dgemm_tn_sub(h, Ut + (kb + b) * ldu + kb, ldu, B + (kb + b) * ldb, ldb, B + kb * ldb, ldb, b, ncols,
+                                  below, 0, stream);
+            if (rc) return rc;
+        }
+        rc = launch_tri_solve<true>(Ut + kb * ldu + kb, ldu, b, B + kb * ldb, ldb, ncols, st);
+        if (rc) return rc;
+    }
+    return GPX_OK;
+}
+
+// ---- rank-1 append: one CTA, x in shared memory, 32-row panels ---------------------------------------
+__global__ void __launch_bounds__(1024, 1) chol_append_kernel(double* __restrict__ U, int n, int64_t ld,
+                                                               const double* __restrict__ knew, double kpp, int* info) {
+    extern __shared__ double x[];  // n entries
+    __shared__ double red[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < n; i += 1024) x[i] = knew[i];
+    __syncthreads();
+    for (int rb = 0; rb < n; rb += 32) {
+        const int b = n - rb < 32 ? n - rb : 32;
+        if (warp == 0) {
+            // solve the 32x32 triangle: lane r owns x[rb+r]
+            double xr = lane < b ? x[rb + lane] : 0.0;
+            for (int s = 0; s < b; ++s) {
+                const double uss = U[(int64_t)(rb + s) * ld + rb + s];
+                const double xs = __shfl_sync(0xffffffffu, xr, s) / uss;
+                if (lane == s) xr = xs;
+                if (lane > s && lane < b) xr = fma(-U[(int64_t)(rb + s) * ld + rb + lane], xs, xr);
+            }
+            if (lane < b) x[rb + lane] = xr;
+        }
+        __syncthreads();
+        for (int i = rb + 32 + tid; i < n; i += 1024) {
+            double v = x[i];
+#pragma unroll 8
+            for (int s = 0; s < 32; ++s) v = fma(-U[(int64_t)(rb + s) * ld + i], x[rb + s], v);
+            x[i] = v;
+        }
+        __syncthreads();
+    }
+    double ss = 0.0;
+    for (int i = tid; i < n; i += 1024) {
+        ss = fma(x[i], x[i], ss);
+        U[(int64_t)i * ld + n] = x[i];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    if (warp == 0) {
+        ss = red[lane];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+        if (lane == 0) {
+            const double d2 = kpp - ss;
+            info[0] = d2 > 0.0 ? 0 : n + 1;
+            U[(int64_t)n * ld + n] = sqrt(d2);
+        }
+    }
+}
+
+extern "C" int gpx_chol_append(gpx_handle h, double* U, int64_t n, int64_t ld, const double* knew, double kpp, int* info,
+                               void* stream) {
+    GPX_REQUIRE(h && U && info && n >= 0 && ld > n, GPX_EINVAL, "bad arguments");
+    GPX_REQUIRE(knew || n == 0, GPX_EINVAL, "knew is NULL");
+    const size_t smem = (size_t)n * sizeof(double);
+    GPX_REQUIRE(smem <= 200 * 1024, GPX_ESIZE, "design size exceeds the shared-memory buffer (25600)");
+    if (smem > 48 * 1024) cudaFuncSetAttribute(chol_append_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    chol_append_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(U, (int)n, ld, knew, kpp, info);
+    return gpx_check_launch("gpx_chol_append");
+}

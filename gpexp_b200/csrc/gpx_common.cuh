@@ -1,0 +1,145 @@
+// Shared declarations of the gpexp_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gpexp_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "gpexp_b200 is written for sm_100a (B200) only"
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// Kernel hyper-parameters.  Passed BY VALUE to every launch as a __grid_constant__ argument, so the
+// ARD length-scales live in the constant bank without a module-global that handles would share.
+// ---------------------------------------------------------------------------------------------
+struct KParams {
+    int family;
+    int d;
+    double signal;            // SE / MATERN32: signalSize ; MEHLER: prod_i (1 - t_i^2)^(-1/2)
+    double c0;                // MATERN32: sqrt(3) / rho
+    double a[GPX_MAX_DIM];    // SE: cl_i^-2            ; MEHLER: t_i^2
+    double b[GPX_MAX_DIM];    // MEHLER: 2 t_i
+    double c[GPX_MAX_DIM];    // MEHLER: 1 / (2 (1 - t_i^2))
+};
+
+struct gpx_context {
+    int device;
+    int sm_count;
+    bool has_kernel;
+    KParams kp;
+    // reduction scratch, all device memory
+    double* red_val;          // GPX_RED_SLOTS doubles
+    int64_t* red_idx;         // GPX_RED_SLOTS indices
+    unsigned int* red_counter;// last-block-done tickets (zero between calls)
+    double* scal;             // a few device scalars (sum of varM ...)
+    int64_t* iscal;
+};
+
+#define GPX_RED_SLOTS 2048
+
+void gpx_set_error(const char* fmt, ...);
+int gpx_check_launch(const char* what);
+
+#define GPX_REQUIRE(cond, code, msg)                 \
+    do {                                             \
+        if (!(cond)) {                               \
+            gpx_set_error("%s: %s", __func__, msg);  \
+            return (code);                           \
+        }                                            \
+    } while (0)
+
+#define GPX_NEED_KERNEL(h) GPX_REQUIRE((h) && (h)->has_kernel, GPX_ENOKERNEL, "gpx_set_kernel has not been called")
+
+static inline bool gpx_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---------------------------------------------------------------------------------------------
+// Difference-form covariance evaluation, one dimension at a time (coordinates come from wherever
+// the caller keeps them: registers, shared memory or strided global memory).
+//   SE       kernels.py:121-122   signal * exp(-1/2 sum (x-y)^2 cl^-2)
+//   MATERN32 kernels.py:87-89     signal * (1 + sqrt3 r / rho) exp(-sqrt3 r / rho)
+//   MEHLER   kernels.py:282-285   prod_i (1-t^2)^(-1/2) exp(-(x^2 t^2 - 2 t x y + y^2 t^2) / (2 (1-t^2)))
+// ---------------------------------------------------------------------------------------------
+template <int FAM>
+__device__ __forceinline__ void kacc_dim(double& acc, const KParams& kp, int i, double x, double y) {
+    if (FAM == GPX_SE) {
+        const double df = x - y;
+        acc = fma(df * df, kp.a[i], acc);
+    } else if (FAM == GPX_MATERN32) {
+        const double df = x - y;
+        acc = fma(df, df, acc);
+    } else {
+        const double num = x * x * kp.a[i] - kp.b[i] * x * y + y * y * kp.a[i];
+        acc = fma(num, kp.c[i], acc);
+    }
+}
+
+template <int FAM>
+__device__ __forceinline__ double kfinish(double acc, const KParams& kp) {
+    if (FAM == GPX_SE) return kp.signal * exp(-0.5 * acc);
+    if (FAM == GPX_MATERN32) {
+        const double t = kp.c0 * sqrt(acc);
+        return kp.signal * (1.0 + t) * exp(-t);
+    }
+    return kp.signal * exp(-acc);
+}
+
+// Expanded form used by the tensor-core prologue:  k = kexpand(alpha(x) + beta(y) + sum_i u_i(x) v_i(y)).
+template <int FAM>
+__device__ __forceinline__ double kexpand(double e, const KParams& kp) {
+    if (FAM == GPX_MATERN32) {
+        const double t = kp.c0 * sqrt(fmax(e, 0.0));
+        return kp.signal * (1.0 + t) * exp(-t);
+    }
+    return kp.signal * exp(e);
+}
+
+#define GPX_DISPATCH_FAMILY(fam, ...)                         \
+    do {                                                      \
+        if ((fam) == GPX_SE) {                                \
+            constexpr int FAM = GPX_SE;                       \
+            __VA_ARGS__;                                      \
+        } else if ((fam) == GPX_MATERN32) {                   \
+            constexpr int FAM = GPX_MATERN32;                 \
+            __VA_ARGS__;                                      \
+        } else {                                              \
+            constexpr int FAM = GPX_MEHLER;                   \
+            __VA_ARGS__;                                      \
+        }                                                     \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// (value, index) ordering of np.argmax / np.argmin: better value wins, ties go to the lower index.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool gpx_better(double v, int64_t i, double bv, int64_t bi, bool minimize) {
+    if (i < 0) return false;
+    if (bi < 0) return true;
+    if (minimize ? (v < bv) : (v > bv)) return true;
+    return (v == bv) && (i < bi);
+}
+
+__device__ __forceinline__ void gpx_warp_argreduce(double& v, int64_t& i, bool minimize) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+        const int64_t oi = __shfl_xor_sync(0xffffffffu, i, off);
+        if (gpx_better(ov, oi, v, i, minimize)) {
+            v = ov;
+            i = oi;
+        }
+    }
+}
+
+// internal launchers shared between translation units
+int gpx_launch_core_ivar(gpx_handle h, const double* Wm, int64_t ldm, const double* Ma_rows, const double* Ma_scal,
+                         int64_t M, const double* Wc, int64_t ldc, const double* Cb_rows, const double* Cb_scal,
+                         int64_t C, int64_t n, double* partial, int64_t ldp, int* nsplit_out, cudaStream_t st);
+int gpx_launch_core_store(gpx_handle h, const double* A, int64_t lda, const double* Ap, const double* As,
+                          int64_t I, const double* B, int64_t ldb, const double* Bp, const double* Bs, int64_t J,
+                          int64_t K, double* out, int64_t ldo, cudaStream_t st);
+int gpx_ivar_splits(gpx_handle h, int64_t M, int64_t C);
+int gpx_argreduce_impl(gpx_handle h, const double* v, const double* weights, const uint8_t* mask, int64_t n,
+                       int minimize, double* best, int64_t* idx, cudaStream_t st);
+int gpx_sum_impl(gpx_handle h, const double* v, int64_t n, double* out, cudaStream_t st);

@@ -1,0 +1,121 @@
+"""Device-side plumbing: one gpx handle per CUDA device, device buffers (torch tensors used only as
+allocations), and thin typed wrappers over the C ABI.  No arithmetic happens in this file."""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GpxError, check, lib
+
+F64 = torch.float64
+PAD = 128  # leading dimensions are multiples of the tensor-core tile (also keeps every row 16-byte aligned)
+
+
+def roundup(n: int, m: int = PAD) -> int:
+    return max(m, (int(n) + m - 1) // m * m)
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+class PointSet:
+    """A set of points resident on the device, dimension-major: X[i, j] = coordinate i of point j."""
+
+    def __init__(self, dev: "Device", X: torch.Tensor, n: int, d: int):
+        self.dev, self.X, self.n, self.d, self.ld = dev, X, n, d, X.shape[1]
+        self._sides = {}
+
+    def side(self, which: int):
+        """Prepared operand (rows, scal) for the tensor-core Gram prologue; cached per kernel epoch."""
+        key = (which, self.dev.kernel_epoch)
+        if key not in self._sides:
+            rows = torch.zeros((_lib.GPX_KROWS, self.ld), dtype=F64, device=self.dev.torch_device)
+            scal = torch.zeros((self.ld,), dtype=F64, device=self.dev.torch_device)
+            check(lib.gpx_prep_side(self.dev.h, which, ptr(self.X), self.n, self.ld, ptr(rows), ptr(scal), self.ld,
+                                    self.dev.stream), "gpx_prep_side")
+            self._sides = {k: v for k, v in self._sides.items() if k[1] == self.dev.kernel_epoch}
+            self._sides[key] = (rows, scal)
+        return self._sides[key]
+
+
+class Device:
+    """Owns the gpx handle of one CUDA device."""
+
+    _instances = {}
+    _lock = threading.Lock()
+
+    @classmethod
+    def get(cls, index=None) -> "Device":
+        if not torch.cuda.is_available():
+            raise GpxError("gpexp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        if index is None:
+            index = torch.cuda.current_device()
+        with cls._lock:
+            if index not in cls._instances:
+                cls._instances[index] = cls(index)
+            return cls._instances[index]
+
+    def __init__(self, index: int):
+        self.index = index
+        self.torch_device = torch.device("cuda", index)
+        torch.cuda.set_device(index)
+        h = C.c_void_p()
+        check(lib.gpx_create(index, C.byref(h)), "gpx_create")
+        self.h = h
+        self.kernel_epoch = 0
+        self._kernel_key = None
+        self.launches = 0  # kernels launched through this handle (bench.py reports it)
+
+    # ---- stream / kernel -------------------------------------------------------------------------
+    @property
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.torch_device).cuda_stream
+
+    def set_kernel(self, family: int, d: int, params) -> None:
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        key = (family, d, params.tobytes())
+        if key == self._kernel_key:
+            return
+        check(lib.gpx_set_kernel(self.h, family, d, params.ctypes.data_as(C.POINTER(C.c_double)), params.size),
+              "gpx_set_kernel")
+        self._kernel_key = key
+        self.kernel_epoch += 1
+
+    # ---- buffers ---------------------------------------------------------------------------------
+    def zeros(self, *shape, dtype=F64) -> torch.Tensor:
+        return torch.zeros(shape, dtype=dtype, device=self.torch_device)
+
+    def empty(self, *shape, dtype=F64) -> torch.Tensor:
+        return torch.empty(shape, dtype=dtype, device=self.torch_device)
+
+    def upload(self, a: np.ndarray, dtype=F64) -> torch.Tensor:
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        return t.to(self.torch_device, non_blocking=False)
+
+    def points(self, pts: np.ndarray) -> PointSet:
+        """Upload row-major (n, d) host points and lay them out dimension-major on the device."""
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        assert pts.ndim == 2, "points must be an (n, d) array"
+        n, d = pts.shape
+        if d > _lib.GPX_MAX_DIM:
+            raise GpxError(f"dimension {d} exceeds GPX_MAX_DIM={_lib.GPX_MAX_DIM}")
+        ld = roundup(n)
+        X = self.zeros(max(d, 1), ld)
+        if n:
+            raw = self.upload(pts)
+            check(lib.gpx_transpose(self.h, ptr(raw), n, d, d, ptr(X), ld, self.stream), "gpx_transpose")
+            self.launches += 1
+        return PointSet(self, X, n, d)
+
+    def points_from_device(self, X: torch.Tensor, n: int, d: int) -> PointSet:
+        return PointSet(self, X, n, d)
+
+    def sync(self) -> None:
+        torch.cuda.current_stream(self.torch_device).synchronize()

@@ -1,0 +1,408 @@
+"""Device-resident greedy design engines.
+
+Every engine keeps its whole state in HBM (W factors, running variances, pivot records, picked
+indices) and advances one greedy step with a fixed, host-sync-free sequence of C-ABI launches; the
+host reads the picked indices back once at the end.  Layouts (all float64):
+
+    X      d x ld        dimension-major coordinates of a point set (ld = roundup(n, 128))
+    W      ncap x ld     row i = i-th row of L^-1 K(D, .) for every point of the set (K-major for DMMA)
+    var    ld            running posterior variance of every point
+    rec    19 + ncap     pivot record: score, global index, var_p + noise, x_p[16], W[0:n, p]
+
+Candidates shard across ranks (one process per GPU): each rank owns a contiguous block of the pool,
+the integration points are replicated, and the only exchange per step is one NCCL all-gather of the
+ranks' pivot records followed by an identical on-device selection (lowest score/highest score, ties
+to the lowest global index) -- so every rank appends bit-identical rows.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib
+from .device import Device, PointSet, F64, ptr, roundup
+
+HDR = _lib.GPX_PIVOT_HDR
+ZERO_VAR_TOL = 1e-13
+
+
+class Shard:
+    """Position of this process in a candidate-sharded job (torch.distributed, NCCL on GPUs)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    @staticmethod
+    def split(n_total: int, world: int, rank: int):
+        """Contiguous block [lo, hi) of rank `rank` (remainder spread over the first ranks)."""
+        base, rem = divmod(n_total, world)
+        lo = rank * base + min(rank, rem)
+        return lo, lo + base + (1 if rank < rem else 0)
+
+    def all_gather(self, out: torch.Tensor, inp: torch.Tensor):
+        self.dist.all_gather_into_tensor(out, inp, group=self.group)
+
+
+def prior_scale(family: int, params) -> float:
+    """k(0,0): the magnitude against which 'numerically zero variance' is judged."""
+    params = np.asarray(params, dtype=np.float64)
+    if family == _lib.SE:
+        return float(abs(params[-1]))
+    if family == _lib.MATERN32:
+        return float(abs(params[1]))
+    return float(np.prod((1.0 - params ** 2.0) ** -0.5))
+
+
+class _Pivoting:
+    """Shared pivot plumbing: gather the local best, exchange across ranks, keep the history."""
+
+    def _init_pivot(self, dev: Device, ncap: int, n_max: int, shard, index_offset: int):
+        self.dev = dev
+        self.ncap = ncap
+        self.n_max = n_max
+        self.n = 0
+        self.shard = shard
+        self.index_offset = index_offset
+        self.reclen = HDR + ncap
+        self.rec = dev.zeros(self.reclen)
+        self.best = dev.zeros(1)
+        self.idx = dev.zeros(1, dtype=torch.int64)
+        self.picks = dev.zeros(max(n_max, 1), dtype=torch.int64)
+        self.pick_scores = dev.zeros(max(n_max, 1))
+        if shard is not None and shard.world > 1:
+            self.rec_all = dev.zeros(shard.world * self.reclen)
+            self.rec_win = dev.zeros(self.reclen)
+        else:
+            self.rec_all = None
+            self.rec_win = self.rec
+
+    def _gather(self, W, ld, var, X: PointSet, noise: float, minimize: bool):
+        dev = self.dev
+        check(lib.gpx_gather_pivot(dev.h, ptr(W), ld, self.n, ptr(var), ptr(X.X), X.ld, ptr(self.best), ptr(self.idx),
+                                   self.index_offset, noise, ptr(self.rec), dev.stream), "gpx_gather_pivot")
+        dev.launches += 1
+        if self.rec_all is not None:
+            self.shard.all_gather(self.rec_all, self.rec)
+            check(lib.gpx_select_pivot(dev.h, ptr(self.rec_all), self.shard.world, self.reclen, self.n,
+                                       1 if minimize else 0, ptr(self.rec_win), dev.stream), "gpx_select_pivot")
+            dev.launches += 1
+
+    def _force_local(self, global_index: int):
+        """Make `global_index` the pivot of this step (seeds / given designs): owner rank points at it."""
+        local = global_index - self.index_offset
+        if not (0 <= local < self._local_count()):
+            local = -1
+        self.idx.fill_(local)
+        self.best.zero_()
+
+    def _record(self, U=None, ldu=0):
+        dev = self.dev
+        check(lib.gpx_store_pivot(dev.h, ptr(self.rec_win), self.n, ptr(U), ldu, ptr(self.picks), ptr(self.pick_scores),
+                                  dev.stream), "gpx_store_pivot")
+        dev.launches += 1
+
+    def indices(self) -> np.ndarray:
+        return self.picks[: self.n].cpu().numpy()
+
+
+class GreedyVarEngine(_Pivoting):
+    """Greedy maximum posterior variance (conditional entropy), experimentalDesign.py:787-845, as an
+    incremental diagonally-pivoted Cholesky of K_CC: per step one arg-max and one HBM-bound row append."""
+
+    def __init__(self, dev: Device, pool: PointSet, n_max: int, weights=None, noise: float = 0.0, shard=None,
+                 index_offset: int = 0):
+        self.pool = pool
+        self.noise = float(noise)
+        ncap = max(int(n_max), 1)
+        self._init_pivot(dev, ncap, n_max, shard, index_offset)
+        self.W = dev.zeros(ncap, pool.ld)
+        self.var = dev.zeros(pool.ld)
+        check(lib.gpx_prior_diag(dev.h, ptr(pool.X), pool.n, pool.ld, ptr(self.var), dev.stream), "gpx_prior_diag")
+        dev.launches += 1
+        self.weights = None if weights is None else dev.upload(np.asarray(weights, dtype=np.float64))
+        self.score_trace = None
+
+    def _local_count(self):
+        return self.pool.n
+
+    def select(self):
+        dev = self.dev
+        check(lib.gpx_argreduce(dev.h, ptr(self.var), ptr(self.weights), None, self.pool.n, 0, ptr(self.best),
+                                ptr(self.idx), dev.stream), "gpx_argreduce")
+        dev.launches += 1
+
+    def append(self):
+        dev, pool = self.dev, self.pool
+        self._gather(self.W, pool.ld, self.var, pool, self.noise, minimize=False)
+        check(lib.gpx_append_row(dev.h, _lib.ROW_KERNEL, ptr(self.rec_win), None, ptr(pool.X), pool.n, pool.ld,
+                                 ptr(self.W), pool.ld, self.n, ptr(self.var), dev.stream), "gpx_append_row")
+        dev.launches += 1
+        self._record()
+        self.n += 1
+
+    def force(self, global_index: int):
+        self._force_local(int(global_index))
+        self.append()
+
+    def step(self):
+        if self.score_trace is not None:
+            v = self.var[: self.pool.n]
+            self.score_trace.append((v * self.weights if self.weights is not None else v).cpu().numpy().copy())
+        self.select()
+        self.append()
+
+    def run(self, n_points: int, progress=None):
+        while self.n < n_points:
+            if progress is not None:
+                progress(self.n)
+            self.step()
+        return self.indices()
+
+
+class DesignFactor:
+    """Cholesky factor of a given design's Gram matrix and the solves built on it (GP class backend):
+    K(D,D) + diag(nugget) = U^T U  (K1 + K2), W = U^-T K(D, X) and posterior variances (K1+K3+K4)."""
+
+    def __init__(self, dev: Device, design: PointSet, nugget):
+        self.dev, self.design = dev, design
+        n = design.n
+        self.n = n
+        self.ldu = design.ld
+        self.U = dev.zeros(max(n, 1), self.ldu)
+        self.info = dev.zeros(1, dtype=torch.int32)
+        nug_vec = None
+        nug = 0.0
+        if isinstance(nugget, np.ndarray):
+            nug_vec = dev.upload(nugget.astype(np.float64).ravel())
+        else:
+            nug = float(nugget)
+        if n:
+            check(lib.gpx_gram(dev.h, ptr(design.X), n, design.ld, ptr(design.X), n, design.ld, ptr(self.U), self.ldu, 1,
+                               ptr(nug_vec), nug, dev.stream), "gpx_gram")
+            self._cov = self.U.clone()
+            check(lib.gpx_potrf(dev.h, ptr(self.U), n, self.ldu, ptr(self.info), dev.stream), "gpx_potrf")
+            dev.launches += 2 + 3 * ((n + 127) // 128)
+        else:
+            self._cov = self.U.clone()
+        self._Ut = None
+
+    def covariance(self) -> np.ndarray:
+        return self._cov[: self.n, : self.n].cpu().numpy()
+
+    def pivot_failure(self) -> int:
+        return int(self.info.item())
+
+    def Ut(self):
+        if self._Ut is None:
+            dev = self.dev
+            self._Ut = dev.zeros(max(self.n, 1), self.ldu)
+            check(lib.gpx_transpose(dev.h, ptr(self.U), self.n, self.n, self.ldu, ptr(self._Ut), self.ldu, dev.stream),
+                  "gpx_transpose")
+            dev.launches += 1
+        return self._Ut
+
+    def solve_gram(self, X: PointSet, W=None, want_var=True):
+        """W = U^-T K(D, X) (n x X.ld) and var = k(x,x) - colsumsq(W)."""
+        dev, D = self.dev, self.design
+        if W is None:
+            W = dev.zeros(max(self.n, 1), X.ld)
+        var = dev.zeros(X.ld) if want_var else None
+        da_rows, da_scal = D.side(_lib.SIDE_A)
+        xb_rows, xb_scal = X.side(_lib.SIDE_B)
+        check(lib.gpx_trsm_gram(dev.h, ptr(self.U), self.n, self.ldu, ptr(da_rows), ptr(da_scal), D.ld, ptr(X.X),
+                                ptr(xb_rows), ptr(xb_scal), X.n, X.ld, ptr(W), X.ld, ptr(var), dev.stream),
+              "gpx_trsm_gram")
+        dev.launches += 2 * ((self.n + 127) // 128) + 2
+        return W, var
+
+    def solve_vector(self, y: np.ndarray) -> np.ndarray:
+        """(U^T U)^-1 y : GP.train coefficients, gp.py:101."""
+        dev = self.dev
+        B = dev.zeros(max(self.n, 1), 2)
+        B[: self.n, 0] = dev.upload(np.asarray(y, dtype=np.float64))
+        check(lib.gpx_trsm(dev.h, ptr(self.U), self.n, self.ldu, ptr(B), 1, 2, dev.stream), "gpx_trsm")
+        check(lib.gpx_trsm_back(dev.h, ptr(self.Ut()), self.n, self.ldu, ptr(B), 1, 2, dev.stream), "gpx_trsm_back")
+        return B[: self.n, 0].cpu().numpy()
+
+    def precision(self) -> np.ndarray:
+        """(U^T U)^-1 as a dense matrix: U^-1 (U^-T I)."""
+        dev, n = self.dev, self.n
+        ld = roundup(n)
+        Y = dev.zeros(max(n, 1), ld)
+        check(lib.gpx_trtri_t(dev.h, ptr(self.U), n, self.ldu, ptr(Y), ld, dev.stream), "gpx_trtri_t")
+        check(lib.gpx_trsm_back(dev.h, ptr(self.Ut()), n, self.ldu, ptr(Y), n, ld, dev.stream), "gpx_trsm_back")
+        return Y[:n, :n].cpu().numpy()
+
+
+class GreedyIVAREngine(_Pivoting):
+    """Discrete greedy IVAR: every step scores all candidates with the FP64 DMMA
+    contraction (K5), takes the arg-min, and appends one row to W_C and W_M."""
+
+    def __init__(self, dev: Device, cand: PointSet, mc: PointSet, n_max: int, noise: float, zero_scale: float,
+                 shard=None, index_offset: int = 0):
+        self.cand, self.mc = cand, mc
+        self.noise = float(noise)
+        self.zero_tol = ZERO_VAR_TOL * float(zero_scale)
+        ncap = max(int(n_max), 1)
+        self._init_pivot(dev, ncap, n_max, shard, index_offset)
+        self.Wc = dev.zeros(ncap, cand.ld)
+        self.Wm = dev.zeros(ncap, mc.ld)
+        self.varC = dev.zeros(cand.ld)
+        self.varM = dev.zeros(mc.ld)
+        self.U = dev.zeros(ncap, roundup(ncap))
+        check(lib.gpx_prior_diag(dev.h, ptr(cand.X), cand.n, cand.ld, ptr(self.varC), dev.stream), "gpx_prior_diag")
+        check(lib.gpx_prior_diag(dev.h, ptr(mc.X), mc.n, mc.ld, ptr(self.varM), dev.stream), "gpx_prior_diag")
+        dev.launches += 2
+        ws = int(lib.gpx_score_ivar_workspace(dev.h, mc.n, cand.n))
+        self.workspace = dev.zeros(max(ws, 1))
+        self.scores = dev.zeros(cand.ld)
+        self.score_trace = None
+
+    def _local_count(self):
+        return self.cand.n
+
+    def score(self):
+        dev, cand, mc = self.dev, self.cand, self.mc
+        ma_rows, ma_scal = mc.side(_lib.SIDE_A)
+        cb_rows, cb_scal = cand.side(_lib.SIDE_B)
+        check(lib.gpx_score_ivar(dev.h, ptr(self.Wm), mc.ld, ptr(self.varM), ptr(ma_rows), ptr(ma_scal), mc.n,
+                                 ptr(self.Wc), cand.ld, ptr(self.varC), ptr(cb_rows), ptr(cb_scal), cand.n, self.n,
+                                 self.noise, self.zero_tol, None, ptr(self.workspace), ptr(self.scores), ptr(self.best),
+                                 ptr(self.idx), dev.stream), "gpx_score_ivar")
+        dev.launches += 4
+
+    def append(self):
+        dev, cand, mc = self.dev, self.cand, self.mc
+        self._gather(self.Wc, cand.ld, self.varC, cand, self.noise, minimize=True)
+        check(lib.gpx_append_row(dev.h, _lib.ROW_KERNEL, ptr(self.rec_win), None, ptr(cand.X), cand.n, cand.ld,
+                                 ptr(self.Wc), cand.ld, self.n, ptr(self.varC), dev.stream), "gpx_append_row")
+        check(lib.gpx_append_row(dev.h, _lib.ROW_KERNEL, ptr(self.rec_win), None, ptr(mc.X), mc.n, mc.ld,
+                                 ptr(self.Wm), mc.ld, self.n, ptr(self.varM), dev.stream), "gpx_append_row")
+        dev.launches += 2
+        self._record(self.U, self.U.shape[1])
+        self.n += 1
+
+    def force(self, global_index: int):
+        self._force_local(int(global_index))
+        self.append()
+
+    def rollback(self, n_keep: int):
+        """Forget the rows appended after n_keep (bench.py re-times the same step)."""
+        assert 0 <= n_keep <= self.n
+        if n_keep == self.n:
+            return
+        dev, cand, mc = self.dev, self.cand, self.mc
+        self.Wc[n_keep: self.n].zero_()
+        self.Wm[n_keep: self.n].zero_()
+        self.n = n_keep
+        prior = dev.zeros(cand.ld)
+        check(lib.gpx_prior_diag(dev.h, ptr(cand.X), cand.n, cand.ld, ptr(prior), dev.stream), "gpx_prior_diag")
+        check(lib.gpx_colsumsq(dev.h, ptr(self.Wc), self.n, cand.n, cand.ld, ptr(prior), ptr(self.varC), dev.stream), "colsumsq")
+        prior = dev.zeros(mc.ld)
+        check(lib.gpx_prior_diag(dev.h, ptr(mc.X), mc.n, mc.ld, ptr(prior), dev.stream), "gpx_prior_diag")
+        check(lib.gpx_colsumsq(dev.h, ptr(self.Wm), self.n, mc.n, mc.ld, ptr(prior), ptr(self.varM), dev.stream), "colsumsq")
+
+    def load_design(self, factor: DesignFactor):
+        """State for a GIVEN design (not grown greedily): W_C, W_M via the fused Gram+TRSM, var via K4."""
+        assert factor.n <= self.ncap
+        self.n = factor.n
+        _, vC = factor.solve_gram(self.cand, W=self.Wc)
+        _, vM = factor.solve_gram(self.mc, W=self.Wm)
+        self.varC.copy_(vC)
+        self.varM.copy_(vM)
+
+    def step(self):
+        self.score()
+        if self.score_trace is not None:
+            self.score_trace.append(self.scores[: self.cand.n].cpu().numpy().copy())
+        self.append()
+
+    def run(self, n_points: int, progress=None):
+        while self.n < n_points:
+            if progress is not None:
+                progress(self.n)
+            self.step()
+        return self.indices()
+
+
+class GreedyMIEngine(_Pivoting):
+    """Greedy mutual information (experimentalDesign.py:753-785 with :252-285 restated):
+    numerator = running posterior variance given A (nugget = noise); denominator from the diagonal of
+    the precision of V minus A, kept current by lazy rank-1 downdates."""
+
+    def __init__(self, dev: Device, pool: PointSet, n_max: int, noise: float):
+        self.pool = pool
+        self.noise = float(noise)
+        ncap = max(int(n_max), 1)
+        self._init_pivot(dev, ncap, n_max, None, 0)
+        v, ld = pool.n, pool.ld
+        self.W = dev.zeros(ncap, ld)          # numerator factor rows
+        self.num = dev.zeros(ld)
+        check(lib.gpx_prior_diag(dev.h, ptr(pool.X), v, ld, ptr(self.num), dev.stream), "gpx_prior_diag")
+        # set-up: K_VV + noise I = U^T U ; Y = U^-T ; pd = diag(P) = colsumsq(Y)
+        K = dev.zeros(v, ld)
+        info = dev.zeros(1, dtype=torch.int32)
+        check(lib.gpx_gram(dev.h, ptr(pool.X), v, ld, ptr(pool.X), v, ld, ptr(K), ld, 1, None, self.noise, dev.stream), "gpx_gram")
+        self.cov = K.clone()
+        check(lib.gpx_potrf(dev.h, ptr(K), v, ld, ptr(info), dev.stream), "gpx_potrf")
+        self.U = K
+        self.Y = dev.zeros(v, ld)
+        check(lib.gpx_trtri_t(dev.h, ptr(K), v, ld, ptr(self.Y), ld, dev.stream), "gpx_trtri_t")
+        self.pd = dev.zeros(ld)
+        check(lib.gpx_colsumsq(dev.h, ptr(self.Y), v, v, ld, None, ptr(self.pd), dev.stream), "gpx_colsumsq")
+        self.info = info
+        self.Us = dev.zeros(ncap, ld)         # downdate vectors u_s
+        self.pcol = dev.zeros(ld)
+        self.rec2 = dev.zeros(self.reclen)
+        self.mask = dev.zeros(ld, dtype=torch.uint8)
+        self.scores = dev.zeros(ld)
+        self.score_trace = None
+        dev.launches += 8 + 6 * ((v + 127) // 128)
+
+    def _local_count(self):
+        return self.pool.n
+
+    def take(self):
+        """Move the point in self.idx from S = V minus A into A."""
+        dev, pool = self.dev, self.pool
+        v, ld = pool.n, pool.ld
+        self._gather(self.W, ld, self.num, pool, self.noise, minimize=False)
+        check(lib.gpx_append_row(dev.h, _lib.ROW_KERNEL, ptr(self.rec), None, ptr(pool.X), v, ld, ptr(self.W), ld, self.n,
+                                 ptr(self.num), dev.stream), "gpx_append_row")
+        check(lib.gpx_mi_prec_column(dev.h, ptr(self.Y), v, ld, ptr(self.idx), ptr(self.pcol), dev.stream), "gpx_mi_prec_column")
+        check(lib.gpx_gather_pivot(dev.h, ptr(self.Us), ld, self.n, ptr(self.pd), ptr(pool.X), ld, None, ptr(self.idx), 0, 0.0,
+                                   ptr(self.rec2), dev.stream), "gpx_gather_pivot")
+        check(lib.gpx_append_row(dev.h, _lib.ROW_MATRIX, ptr(self.rec2), ptr(self.pcol), None, v, ld, ptr(self.Us), ld, self.n,
+                                 ptr(self.pd), dev.stream), "gpx_append_row")
+        check(lib.gpx_set_mask(dev.h, ptr(self.mask), ptr(self.idx), 1, dev.stream), "gpx_set_mask")
+        dev.launches += 6
+        self._record()
+        self.n += 1
+
+    def force(self, index: int):
+        self._force_local(int(index))
+        self.take()
+
+    def score(self):
+        dev = self.dev
+        check(lib.gpx_score_mi(dev.h, ptr(self.num), ptr(self.pd), self.noise, ptr(self.mask), self.pool.n, ptr(self.scores),
+                               ptr(self.best), ptr(self.idx), dev.stream), "gpx_score_mi")
+        dev.launches += 2
+
+    def step(self):
+        self.score()
+        if self.score_trace is not None:
+            self.score_trace.append(self.scores[: self.pool.n].cpu().numpy().copy())
+        self.take()
+
+    def run(self, n_points: int, start: int = 0):
+        if self.n == 0:
+            self.force(start)
+        while self.n < n_points:
+            self.step()
+        return self.indices()

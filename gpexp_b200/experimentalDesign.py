@@ -1,0 +1,215 @@
+"""Cost functions and discrete greedy design drivers with the reference's names and signatures
+(gpExp/experimentalDesign.py), running on the device-resident engines of gpexp_b200.engine.
+
+    costFunctionGP_IVAR                     experimentalDesign.py:60-117   (version 1, MC-integrated variance)
+    costFunctionGP_MI                       experimentalDesign.py:223-285
+    performGreedyVarExperimentalDesign      experimentalDesign.py:787-845
+    performGreedyMIExperimentalDesign       experimentalDesign.py:753-785
+    performGreedyIVARExperimentalDesign     NEW: the discrete greedy-IVAR driver the north star asks for; the
+                                            reference only has the cost function
+
+The continuous optimisers, the eigen-basis IVAR (version 0, dead code in the reference), the clustering
+design and the Bayesian-optimisation costs are out of scope.
+"""
+import copy
+import itertools
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+from .device import Device, ptr
+from .engine import (DesignFactor, GreedyIVAREngine, GreedyMIEngine, GreedyVarEngine, Shard, prior_scale)
+from .gp_kernel_utilities import _nugget_arg
+
+VERBOSE = True  # the reference prints its progress unconditionally (experimentalDesign.py:812-813)
+
+
+class costFunctionBase(object):
+
+    def __init__(self, nInputs, space):
+        self.numInputs = nInputs
+        self.space = space
+
+
+class costFunctionGP_IVAR(costFunctionBase):
+    """Integrated posterior variance of a design, Monte-Carlo version (version=1)."""
+
+    def __init__(self, gaussianProcess, nInputs, space, version=1, **kwargs):
+        super(costFunctionGP_IVAR, self).__init__(nInputs, space)
+        self.gaussianProcess = copy.copy(gaussianProcess)
+        self.version = version
+        if self.version == 1:
+            if 'mcPoints' in kwargs:
+                self.mcPoints = kwargs['mcPoints']
+                self.nMC = len(self.mcPoints)
+            else:
+                self.nMC = 10000
+                self.mcPoints = space.sample((self.nMC, space.dimension))
+        else:
+            raise NotImplementedError("IVAR version 0 needs a kernel eigen-basis that no shipped kernel "
+                                      "provides (experimentalDesign.py:119-146 is unreachable)")
+        self._mc_dev = None
+
+    def _mc_points(self, dev):
+        if self._mc_dev is None or self._mc_dev.dev is not dev:
+            self._mc_dev = dev.points(self.mcPoints)
+        return self._mc_dev
+
+    def evaluate(self, inputPoints):
+        """|mean posterior variance over the MC points| for the design `inputPoints` (:79-117)."""
+        assert inputPoints.shape == (self.numInputs, self.space.dimension), \
+            ("inputPoints are the wrong size: ", inputPoints.shape)
+        gp = self.gaussianProcess
+        if self.space.noiseFunc is None:
+            gp.addNodesAndComputeCovariance(inputPoints)
+        else:
+            addNoise = self.space.noiseFunc(inputPoints)
+            gp.addNodesAndComputeCovariance(inputPoints, addNoise)
+        f = gp._factor
+        mc = self._mc_points(f.dev)
+        _, var = f.solve_gram(mc)
+        total = f.dev.zeros(1)
+        check(lib.gpx_sum(f.dev.h, ptr(var), mc.n, ptr(total), f.dev.stream), "gpx_sum")
+        f.dev.launches += 1
+        cost = 1.0 / float(self.nMC) * float(total.item())
+        return np.abs(cost)
+
+
+class costFunctionGP_MI(costFunctionBase):
+    """Krause-Guestrin mutual-information ratio var(y|A) / var(y|V minus A minus y)."""
+
+    def __init__(self, gaussianProcess, nInputs, space, nmc=None, mcpoints=None, square=False):
+        super(costFunctionGP_MI, self).__init__(nInputs, space)
+        self.gaussianProcess = gaussianProcess  # aliased, not copied (experimentalDesign.py:227)
+        if nmc is not None:
+            self.nMC = nmc
+            self.mcPoints = np.copy(mcpoints)
+        else:
+            if space.dimension == 2 and square is True:
+                x = np.linspace(-1, 1, 10)
+                self.nMC = len(x) * len(x)
+                self.mcPoints = np.array(list(itertools.product(x, x)))
+            else:
+                self.nMC = 200
+                self.mcPoints = space.sample((self.nMC, space.dimension))
+        self.gaussianProcess.addNodesAndComputeCovariance(self.mcPoints)
+        self._engine = None
+
+    def add_candidates(self, nCandidates, candidates):
+        self.nMC = nCandidates
+        self.mcPoints = copy.deepcopy(candidates)
+        self.gaussianProcess.addNodesAndComputeCovariance(self.mcPoints)
+        self._engine = None
+
+    # the reference stores these at construction and never reads them again (:241-242)
+    @property
+    def cov(self):
+        return self.gaussianProcess.covarianceMatrix
+
+    @property
+    def invcov(self):
+        return self.gaussianProcess.precisionMatrix
+
+    def _new_engine(self, n_max):
+        gp = self.gaussianProcess
+        noise = _nugget_arg(gp.noise)
+        if isinstance(noise, np.ndarray):
+            raise NotImplementedError("MI with per-point noise is not supported on the device path")
+        dev = gp.kernel._bind()
+        pool = dev.points(self.mcPoints)
+        return GreedyMIEngine(dev, pool, n_max, float(noise))
+
+    def evaluate(self, index, indexAdded):
+        """MI ratio of candidate `index` given the already chosen `indexAdded` (:252-285); shape (1,)."""
+        eng = self._new_engine(len(indexAdded) + 1)
+        for i in indexAdded:
+            eng.force(int(i))
+        eng.score()
+        return eng.scores[int(index): int(index) + 1].cpu().numpy()
+
+
+def performGreedyMIExperimentalDesign(costFuncMI, nPoints, start=0):
+    """Greedy MI design over the cost function's pool (experimentalDesign.py:753-785).
+    Returns the chosen POINTS (as the reference does); the indices are left in
+    `costFuncMI.lastIndices`."""
+    eng = costFuncMI._new_engine(nPoints)
+    idx = eng.run(nPoints, start=start)
+    costFuncMI.lastIndices = idx
+    costFuncMI._engine = eng
+    return costFuncMI.mcPoints[idx, :]
+
+
+def performGreedyVarExperimentalDesign(kernel, mcPoints, nPoints, dimension, weights=None, indKeepStart=[]):
+    """Greedy maximum-posterior-variance design (experimentalDesign.py:787-845).
+
+    Same contract as the reference: returns mcPoints[indKeep, :]; `indKeepStart` seeds the design and
+    is extended in place (the reference mutates the caller's list, :808); selected points stay in the
+    pool; the nugget is 0.0 (:825).
+    """
+    if indKeepStart == []:
+        indKeep = []
+    else:
+        indKeep = indKeepStart
+    dev = kernel._bind()
+    pool = dev.points(mcPoints)
+    eng = GreedyVarEngine(dev, pool, max(nPoints, len(indKeep)), weights=weights, noise=0.0)
+    for seed in list(indKeep):
+        eng.force(int(seed))
+
+    def progress(have):
+        if VERBOSE and have % 10 == 0:
+            print("Number of points we have ", have)
+
+    idx = eng.run(nPoints, progress=progress)
+    for i in idx[len(indKeep):]:
+        indKeep.append(int(i))
+    return mcPoints[indKeep, :]
+
+
+def performGreedyIVARExperimentalDesign(costFuncIVAR, candidates, nPoints, returnIndices=False, shard=None):
+    """Discrete greedy IVAR: at every step score `costFuncIVAR.evaluate(design + [c])` for every candidate
+    c and add the arg-min -- what a loop over costFunctionGP_IVAR.evaluate (experimentalDesign.py:79-117)
+    computes, restated with the Schur identity and run as one FP64 tensor-core contraction per step.
+
+    candidates : (C, d) array.  With `shard` (a gpexp_b200.engine.Shard) every rank passes the FULL
+    candidate array and scores its own contiguous block.
+    """
+    gp = costFuncIVAR.gaussianProcess
+    if costFuncIVAR.space.noiseFunc is not None:
+        raise NotImplementedError("greedy IVAR with a heteroscedastic noise function is not on the device path")
+    noise = _nugget_arg(gp.noise)
+    if isinstance(noise, np.ndarray):
+        raise NotImplementedError("greedy IVAR needs a scalar noise")
+    dev = gp.kernel._bind()
+    fam, d, params = gp.kernel._gpx_spec()
+    lo, hi = 0, candidates.shape[0]
+    if shard is not None:
+        lo, hi = Shard.split(candidates.shape[0], shard.world, shard.rank)
+    cand = dev.points(candidates[lo:hi])
+    mc = dev.points(costFuncIVAR.mcPoints)
+    eng = GreedyIVAREngine(dev, cand, mc, nPoints, float(noise), prior_scale(fam, params), shard=shard, index_offset=lo)
+    idx = eng.run(nPoints)
+    costFuncIVAR.lastIndices = idx
+    costFuncIVAR.lastScores = eng.pick_scores[: eng.n].cpu().numpy()
+    if returnIndices:
+        return idx
+    return candidates[idx, :]
+
+
+def scoreCandidatesIVAR(costFuncIVAR, design, candidates):
+    """One stateless IVAR scoring pass from HOST buffers: cost of design + [c] for every candidate c.
+    Returns (costs (C,), argmin index).  This is the end-to-end call bench.py times (`e2e`)."""
+    gp = costFuncIVAR.gaussianProcess
+    noise = _nugget_arg(gp.noise)
+    dev = gp.kernel._bind()
+    fam, d, params = gp.kernel._gpx_spec()
+    cand = dev.points(candidates)
+    mc = dev.points(costFuncIVAR.mcPoints)
+    n = design.shape[0]
+    eng = GreedyIVAREngine(dev, cand, mc, max(n, 1), float(noise), prior_scale(fam, params))
+    if n:
+        eng.load_design(DesignFactor(dev, dev.points(design), float(noise)))
+    eng.score()
+    costs = eng.scores[: cand.n].cpu().numpy()
+    return costs, int(eng.idx.item())

@@ -1,0 +1,208 @@
+/*
+ * gpexp_b200 -- C ABI of the B200-native greedy experimental-design hot path.
+ *
+ * The reference (goroda/GPEXP) is pure Python/numpy and has NO native or FFI layer
+ * (SURVEY.md section 8b), so there is no existing binding to mirror: every entry point
+ * below cites the reference Python function whose arithmetic it replaces, and
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host;
+ *     the library never frees caller memory and allocates nothing after gpx_create;
+ *   - all arithmetic is IEEE float64;
+ *   - point sets are stored dimension-major ("SoA"): coordinate i of point j is X[i*ldx + j];
+ *   - matrices are row-major with an explicit leading dimension; leading dimensions and
+ *     column offsets handed to the tensor-core routines must be even (16-byte rows);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream and
+ *     never synchronise the device unless stated;
+ *   - return value: 0 = OK, <0 = bad argument (GPX_E*), >0 = cudaError_t of a failed launch;
+ *     gpx_last_error() returns a thread-local host string;
+ *   - no exceptions, no exit(), re-entrant per handle, one handle per device.
+ */
+#ifndef GPEXP_B200_H
+#define GPEXP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPX_VERSION 100
+
+#define GPX_MAX_DIM 16 /* largest supported input dimension                              */
+#define GPX_KROWS 16   /* rows of a prepared side: GPX_MAX_DIM, zero padded                */
+
+/* kernel families (gpExp/kernels.py) */
+#define GPX_SE 0       /* KernelSquaredExponential, iso or ARD      kernels.py:100-123     */
+#define GPX_MATERN32 1 /* KernelIsoMatern, nu = 3/2                 kernels.py:72-91       */
+#define GPX_MEHLER 2   /* KernelMehlerND / KernelMehler1D           kernels.py:183-293     */
+
+/* error codes */
+#define GPX_OK 0
+#define GPX_EINVAL (-1)    /* bad argument                                                   */
+#define GPX_EALIGN (-2)    /* pointer / leading dimension not 16-byte aligned                */
+#define GPX_ENOKERNEL (-3) /* gpx_set_kernel not called                                      */
+#define GPX_ESIZE (-4)     /* size exceeds a documented limit                                */
+
+/* sides of a prepared point set for the tensor-core Gram prologue */
+#define GPX_SIDE_A 0 /* the "row" operand (integration points / design rows)                  */
+#define GPX_SIDE_B 1 /* the "column" operand (candidates / query points)                      */
+
+/* row sources of gpx_append_row */
+#define GPX_ROW_KERNEL 0 /* new row starts from k(x_p, y_j)                                   */
+#define GPX_ROW_MATRIX 1 /* new row starts from a given device row (MI precision downdate)    */
+
+typedef struct gpx_context* gpx_handle;
+
+int gpx_version(void);
+const char* gpx_last_error(void);
+
+/* One handle per device.  Allocates a small reduction scratch; nothing else. */
+int gpx_create(int device, gpx_handle* out);
+int gpx_destroy(gpx_handle h);
+
+/* Kernel family + hyper-parameters.  They travel to every launch as a __grid_constant__ struct,
+ * i.e. they live in the constant bank (ARD length-scales in constant memory).
+ *   GPX_SE       params_host = cl[0..d) , signalSize           (nparams = d+1)  kernels.py:103-111
+ *   GPX_MATERN32 params_host = rho, signalSize                 (nparams = 2)    kernels.py:74-78
+ *   GPX_MEHLER   params_host = t[0..d)                          (nparams = d)    kernels.py:185-189 */
+int gpx_set_kernel(gpx_handle h, int family, int d, const double* params_host, int nparams);
+
+/* a1  Kernel.evaluate (kernels.py:49-65): out[j] = k(X[j], Y[j]); nx == ny, or one of them 1
+ *     (the (1,d) broadcast that the reference does with np.tile).  out has max(nx,ny) entries. */
+int gpx_kernel_pairwise(gpx_handle h, const double* X, int64_t nx, int64_t ldx, const double* Y, int64_t ny,
+                        int64_t ldy, double* out, void* stream);
+
+/* k(x,x) per point: the prior variance the cost functions start from (gp.py:251,
+ * experimentalDesign.py:816-818, :260). */
+int gpx_prior_diag(gpx_handle h, const double* X, int64_t n, int64_t ldx, double* out, void* stream);
+
+/* K1 / a5  calculateCovarianceMatrix (gp_kernel_utilities.py:34-68) generalised to a cross block:
+ *     out[i*ld + j] = k(X[i], Y[j]) ; if add_diag: out[i*ld+i] += nugget_vec ? nugget_vec[i] : nugget.
+ *     Difference form (x-y)^2, one pass, coalesced stores. */
+int gpx_gram(gpx_handle h, const double* X, int64_t nx, int64_t ldx, const double* Y, int64_t ny, int64_t ldy,
+             double* out, int64_t ld, int add_diag, const double* nugget_vec, double nugget, void* stream);
+
+/* K2  Blocked Cholesky of the symmetric row-major matrix A (upper triangle read):  A = U^T U,
+ *     U upper-triangular written in place (strictly-lower part left untouched).  Replaces
+ *     np.linalg.pinv at gp.py:181 / experimentalDesign.py:268,280,826 for positive-definite Grams.
+ *     info[0] = 0 or (1 + index of the first non-positive pivot). */
+int gpx_potrf(gpx_handle h, double* A, int64_t n, int64_t ld, int* info, void* stream);
+
+/* K2  Rank-1 append: given U (n x n) and the new column knew[0..n) = k(D, x_new), kpp = k(x,x)+nugget,
+ *     writes U[0..n, n] = U^-T knew and U[n,n] = sqrt(kpp - |.|^2).  info as gpx_potrf. */
+int gpx_chol_append(gpx_handle h, double* U, int64_t n, int64_t ld, const double* knew, double kpp, int* info,
+                    void* stream);
+
+/* Prepared side of a point set for the tensor-core Gram prologue: k(x,y) = f(alpha(x)+beta(y)+sum_i u_i(x) v_i(y)).
+ *     rows  : GPX_KROWS x ld, rows >= d zero ; scal : ld entries. */
+int gpx_prep_side(gpx_handle h, int side, const double* X, int64_t n, int64_t ldx, double* rows, double* scal,
+                  int64_t ld, void* stream);
+
+/* K1+K3  W = U^-T K(D, Y) without materialising K(D,Y):  left-looking blocked TRSM whose block rows are
+ *     produced by the DMMA contraction kernel with the Gram evaluated in its prologue.  Replaces
+ *     np.dot(precision, kernelvals) at gp.py:253-255 / experimentalDesign.py:836-837.
+ *     Da_* / Yb_* are prepared sides (GPX_SIDE_A of the design with leading dimension ldd == ldu,
+ *     GPX_SIDE_B of the query points with leading dimension ldw).
+ *     var_out (nullable): var[j] = k(y_j,y_j) - sum_i W[i,j]^2     (K4, a7 GP.evaluateVariance). */
+int gpx_trsm_gram(gpx_handle h, const double* U, int64_t n, int64_t ldu, const double* Da_rows,
+                  const double* Da_scal, int64_t ldd, const double* Y, const double* Yb_rows, const double* Yb_scal,
+                  int64_t ny, int64_t ldy, double* W, int64_t ldw, double* var_out, void* stream);
+
+/* In-place B <- U^-T B for a materialised right-hand side (n x ncols). */
+int gpx_trsm(gpx_handle h, const double* U, int64_t n, int64_t ldu, double* B, int64_t ncols, int64_t ldb,
+             void* stream);
+
+/* In-place B <- U^-1 B (back substitution), used for GP.train coefficients (gp.py:101) and the precision
+ * matrix.  Ut is the TRANSPOSE of U (lower-triangular, row-major; make it with gpx_transpose) so that the
+ * block update operand is K-major for the tensor-core routine. */
+int gpx_trsm_back(gpx_handle h, const double* Ut, int64_t n, int64_t ldu, double* B, int64_t ncols, int64_t ldb,
+                  void* stream);
+
+/* Y = U^-T as an explicit lower-triangular row-major matrix (zero above the diagonal).  MI set-up:
+ * diag((K+noise I)^-1) = column sums of squares of Y, columns of the precision come from gpx_mi_prec_column. */
+int gpx_trtri_t(gpx_handle h, const double* U, int64_t n, int64_t ldu, double* Y, int64_t ldy, void* stream);
+
+/* C[i,j] -= sum_k A[k*lda+i] * B[k*ldb+j]   (i<I, j<J, k<K), FP64 DMMA.  upper_only != 0 skips tiles
+ * strictly below the diagonal (symmetric rank-k update of the Cholesky trailing matrix). */
+int gpx_dgemm_tn_sub(gpx_handle h, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                     int64_t ldc, int64_t I, int64_t J, int64_t K, int upper_only, void* stream);
+
+/* Pivot record: what one greedy step needs to know about the chosen point.  Layout (doubles):
+ *   [0] score  [1] global index (exact integer < 2^53)  [2] var_D(p) + noise (the squared divisor)
+ *   [3 .. 3+GPX_MAX_DIM) coordinates of x_p   [GPX_PIVOT_HDR .. GPX_PIVOT_HDR + n) column W[0..n, p]   */
+#define GPX_PIVOT_HDR (3 + GPX_MAX_DIM)
+
+/* Fill a pivot record from the local candidate `*idx_dev` (device int64, local index):
+ *     rec[1] = *idx_dev + index_offset, rec[0] = *score_dev. */
+int gpx_gather_pivot(gpx_handle h, const double* W, int64_t ldw, int64_t n, const double* var, const double* X,
+                     int64_t ldx, const double* score_dev, const int64_t* idx_dev, int64_t index_offset,
+                     double noise, double* rec, void* stream);
+
+/* Pick the winning record among `nrec` records spaced `stride` doubles apart (NCCL all-gather output):
+ * lowest score if minimize else highest, ties -> lowest global index (np.argmax / np.argmin order). */
+int gpx_select_pivot(gpx_handle h, const double* recs, int nrec, int64_t stride, int64_t n, int minimize,
+                     double* rec_out, void* stream);
+
+/* K3+K4 incremental: append row n of W for every column j < ncols and update the running variance
+ *     w = (src_j - sum_{i<n} rec.col[i] * W[i,j]) / sqrt(rec[2]);  W[n,j] = w;  var[j] -= w*w
+ *     src_j = k(x_p, Y[j]) (GPX_ROW_KERNEL; experimentalDesign.py:829-837, gp.py:246-256 restated
+ *     incrementally) or src_row[j] (GPX_ROW_MATRIX).  HBM-bound: reads 8*n*ncols bytes. */
+int gpx_append_row(gpx_handle h, int row_source, const double* rec, const double* src_row, const double* Y,
+                   int64_t ncols, int64_t ldy, double* W, int64_t ldw, int64_t n, double* var, void* stream);
+
+/* K7  arg-reduce with np.argmax/np.argmin tie-break (lowest index).  score_j = v[j] * (weights?weights[j]:1);
+ *     entries with mask[j] != 0 are skipped.  best[0] = score, idx[0] = local index (-1 if all masked). */
+int gpx_argreduce(gpx_handle h, const double* v, const double* weights, const uint8_t* mask, int64_t n,
+                  int minimize, double* best, int64_t* idx, void* stream);
+
+/* Deterministic sum of n doubles (fixed tree order). */
+int gpx_sum(gpx_handle h, const double* v, int64_t n, double* out, void* stream);
+
+/* Workspace (doubles) gpx_score_ivar needs for C candidates. */
+int64_t gpx_score_ivar_workspace(gpx_handle h, int64_t M, int64_t C);
+
+/* K5+K7  IVAR cost of design+{c} for every candidate c (restates the per-candidate
+ *     costFunctionGP_IVAR.evaluate loop, experimentalDesign.py:105-117 -> gp.py:178-181,246-256):
+ *         r[c]     = sum_m ( k(m,c) - sum_{i<n} Wm[i,m] Wc[i,c] )^2            FP64 DMMA contraction
+ *         cost[c]  = | sum(varM)/M - (r[c] / (varC[c] + noise)) / M |           (reduction = 0 if the
+ *                    denominator is numerically zero: the pinv null-direction rule)
+ *     then arg-min with lowest-index tie-break into best/idx.
+ *     Ma_* : GPX_SIDE_A prepared integration points (leading dimension ldm);
+ *     Cb_* : GPX_SIDE_B prepared candidates (leading dimension ldc). */
+int gpx_score_ivar(gpx_handle h, const double* Wm, int64_t ldm, const double* varM, const double* Ma_rows,
+                   const double* Ma_scal, int64_t M, const double* Wc, int64_t ldc, const double* varC,
+                   const double* Cb_rows, const double* Cb_scal, int64_t C, int64_t n, double noise,
+                   double zero_tol, const uint8_t* mask, double* workspace, double* score_out, double* best,
+                   int64_t* idx, void* stream);
+
+/* K6  MI score = num_var[j] / (1/prec_diag[j] - noise), arg-max over unmasked j
+ *     (experimentalDesign.py:259-285 restated: denominator = 1/[(K_SS+noise I)^-1]_yy - noise). */
+int gpx_score_mi(gpx_handle h, const double* num_var, const double* prec_diag, double noise, const uint8_t* mask,
+                 int64_t n, double* score_out, double* best, int64_t* idx, void* stream);
+
+/* K6  column p of P = Y^T Y for the lower-triangular Y = U^-T (row-major):  out[i] = sum_k Y[k,i] Y[k,p]. */
+int gpx_mi_prec_column(gpx_handle h, const double* Y, int64_t n, int64_t ldy, const int64_t* p_dev, double* out,
+                       void* stream);
+
+/* Column sums of squares: out[j] = sum_{i<n} W[i,j]^2 (optionally out[j] = base[j] - that). */
+int gpx_colsumsq(gpx_handle h, const double* W, int64_t n, int64_t ncols, int64_t ldw, const double* base,
+                 double* out, void* stream);
+
+/* Small utilities the host layer needs so that no arithmetic runs on the CPU. */
+int gpx_transpose(gpx_handle h, const double* in, int64_t rows, int64_t cols, int64_t ld_in, double* out,
+                  int64_t ld_out, void* stream);
+int gpx_set_mask(gpx_handle h, uint8_t* mask, const int64_t* idx_dev, uint8_t value, void* stream);
+int gpx_store_pivot(gpx_handle h, const double* rec, int64_t n, double* U, int64_t ldu, int64_t* picks,
+                    double* scores, void* stream);
+
+/* Yard-stick kernels used only by bench.py to establish the FP64 ceilings on the box. */
+int gpx_bench_dmma(gpx_handle h, int64_t iters, double* sink, void* stream);
+int gpx_bench_dfma(gpx_handle h, int64_t iters, double* sink, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPEXP_B200_H */

@@ -352,9 +352,11 @@ def fast_ivar_scores(kern, cand, mc, w_m, var_m, w_c, var_c, noise, block=4096):
 ZERO_VAR_TOL = 1e-13
 
 
-def kern_scale(kern, pts):
-    """Magnitude of the prior variance, used only to decide 'numerically zero'."""
-    return float(np.max(np.abs(kern.prior(pts[:1])))) if pts.shape[0] else 1.0
+def kern_scale(kern, pts=None):
+    """k(0,0): magnitude of the prior variance, used only to decide 'numerically zero'."""
+    if kern.family == MEHLER:
+        return float(np.prod((1.0 - kern.t ** 2.0) ** -0.5))
+    return abs(kern.signal)
 
 
 def fast_greedy_ivar(kern, cand, mc, n_points, noise):

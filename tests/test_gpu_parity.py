@@ -1,0 +1,429 @@
+"""GPU parity tests: the CUDA path (through the Python API -> ctypes -> C ABI) against
+(1) golden vectors produced by the unmodified reference (tests/golden/*.npz),
+(2) the CPU oracle (oracle/gpexp_oracle.py) at sizes the reference cannot reach,
+(3) size-independent properties (factor reconstruction, round trips, tie-breaking).
+
+Tolerances: indices identical; scores / variances within 1e-9 relative (north star), widened only
+where the reference's own pinv round-off is larger (cond * eps) -- written at each use.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import gpexp_oracle as orc
+from tests.cases import KERNEL_NAMES, product_kernel, spec
+
+pytestmark = pytest.mark.gpu
+
+EPS = 2.220446049250313e-16
+
+
+def keys(z, prefix):
+    return sorted({k.split("/")[1] for k in z.files if k.startswith(prefix + "/")})
+
+
+@pytest.fixture(scope="module")
+def gx():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device; the product path has no CPU fallback")
+    import gpexp_b200.experimentalDesign as ed
+    ed.VERBOSE = False
+    from gpexp_b200 import _lib, device, engine
+    from gpexp_b200 import gp as gpmod
+    from gpexp_b200 import gp_kernel_utilities as gku
+    from gpexp_b200.approximation import Space
+
+    class NS:
+        pass
+    ns = NS()
+    ns.torch, ns.ed, ns.lib, ns._lib, ns.device, ns.engine, ns.gp, ns.gku, ns.Space = \
+        torch, ed, _lib.lib, _lib, device, engine, gpmod, gku, Space
+    ns.dev = device.Device.get(0)
+    ns.ptr = device.ptr
+    ns.check = _lib.check
+    return ns
+
+
+def bind(gx, name):
+    k = product_kernel(name)
+    k._bind(gx.dev)
+    return k
+
+
+# ------------------------------------------------------------------------------------------------
+# golden vectors of the reference
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", KERNEL_NAMES)
+def test_kernel_pairwise_golden(gx, golden, name):
+    z = golden("kernels")
+    k = product_kernel(name)
+    x1, x2, one = z[f"kern/{name}/x1"], z[f"kern/{name}/x2"], z[f"kern/{name}/one"]
+    np.testing.assert_allclose(k.evaluate(x1, x2), z[f"kern/{name}/pair"], rtol=1e-13, atol=1e-300)
+    np.testing.assert_allclose(k.evaluate(x1, one), z[f"kern/{name}/bcast_right"], rtol=1e-13, atol=1e-300)
+    np.testing.assert_allclose(k.evaluate(one, x2), z[f"kern/{name}/bcast_left"], rtol=1e-13, atol=1e-300)
+    np.testing.assert_allclose(k.evaluate(x1, x1), z[f"kern/{name}/prior"], rtol=1e-13)
+    with pytest.raises(AssertionError):
+        k.evaluate(x1[:, :0], x2)
+    with pytest.raises(AssertionError):
+        k.evaluate(x1[:5], x2[:7])
+
+
+def test_gram_golden(gx, golden):
+    z = golden("gram")
+    for name in keys(z, "gram"):
+        k = product_kernel(name)
+        pts, nug = z[f"gram/{name}/pts"], z[f"gram/{name}/nugvec"]
+        np.testing.assert_allclose(gx.gku.calculateCovarianceMatrix(k, pts), z[f"gram/{name}/K0"], rtol=1e-13, atol=1e-300)
+        np.testing.assert_allclose(gx.gku.calculateCovarianceMatrix(k, pts, 1e-3), z[f"gram/{name}/Kscalar"], rtol=1e-13, atol=1e-300)
+        np.testing.assert_allclose(gx.gku.calculateCovarianceMatrix(k, pts, nug), z[f"gram/{name}/Kvec"], rtol=1e-13, atol=1e-300)
+        with pytest.raises(NameError):
+            gx.gku.calculateCovarianceMatrix(k, pts, 1)
+
+
+def test_gp_golden(gx, golden):
+    z = golden("gp")
+    for name in [n for n in keys(z, "gp") if n != "hetero"]:
+        k = product_kernel(name)
+        nodes, query = z[f"gp/{name}/nodes"], z[f"gp/{name}/query"]
+        noise, cond = float(z[f"gp/{name}/noise"]), float(z[f"gp/{name}/cond"])
+        # Cholesky vs the reference's pinv agree to ~cond*eps; never tighter than 1e-9
+        tol = max(1e-9, 50 * cond * EPS)
+        g = gx.gp.GP(k, noise)
+        g.train(nodes, z[f"gp/{name}/fvals"])
+        scale = float(np.max(np.abs(z[f"gp/{name}/absvar"])) + np.max(np.abs(z[f"gp/{name}/cov"])))
+        np.testing.assert_allclose(g.covarianceMatrix, z[f"gp/{name}/cov"], rtol=1e-13, atol=1e-300)
+        var = g.evaluateVariance(query, parallel=0)
+        assert np.max(np.abs(var - z[f"gp/{name}/var"])) <= tol * scale, name
+        mean, absvar = g.evaluate(query, compvar=1)
+        assert np.max(np.abs(absvar - z[f"gp/{name}/absvar"])) <= tol * scale
+        mscale = np.max(np.abs(z[f"gp/{name}/mean"]))
+        assert np.max(np.abs(mean - z[f"gp/{name}/mean"])) <= tol * mscale * 10
+        mean2, cov = g.evaluate(query[:25], compvar=2)
+        assert np.max(np.abs(cov - z[f"gp/{name}/cov25"])) <= tol * scale
+        np.testing.assert_allclose(mean2, mean[:25], rtol=1e-12, atol=1e-12 * mscale)
+        cscale = np.max(np.abs(z[f"gp/{name}/coeff"]))
+        assert np.max(np.abs(g.coeff - z[f"gp/{name}/coeff"])) <= tol * cscale * 10
+        prec = g.precisionMatrix
+        assert np.max(np.abs(prec - z[f"gp/{name}/prec"])) <= tol * np.max(np.abs(z[f"gp/{name}/prec"])) * 10
+        space = gx.Space(k.dimension, None, None, noise=None)
+        cf = gx.ed.costFunctionGP_IVAR(g, nodes.shape[0], space, mcPoints=z[f"gp/{name}/mc"])
+        ref_cost = float(z[f"gp/{name}/ivar_cost"])
+        assert abs(cf.evaluate(nodes) - ref_cost) <= tol * max(ref_cost, 1e-3), name
+        with pytest.raises(AssertionError):
+            cf.evaluate(nodes[:-1])
+    # heteroscedastic branch (experimentalDesign.py:110-114)
+    k = product_kernel("se_ard_2d_wide")
+    nodes, mc = z["gp/hetero/nodes"], z["gp/hetero/mc"]
+    space = gx.Space(2, None, None, noise=lambda p: 1e-4 + 1e-3 * (p[:, 0] ** 2))
+    cf = gx.ed.costFunctionGP_IVAR(gx.gp.GP(k, 1e-6), 25, space, mcPoints=mc)
+    got = cf.evaluate(nodes)
+    assert abs(got - float(z["gp/hetero/ivar_cost"])) <= 1e-9 * got
+
+
+def _trace_var(gx, name, pool, n, weights, seeds):
+    k = bind(gx, name)
+    p = gx.dev.points(pool)
+    eng = gx.engine.GreedyVarEngine(gx.dev, p, n, weights=weights)
+    eng.score_trace = []
+    for s in seeds:
+        eng.force(int(s))
+    idx = eng.run(n)
+    return idx, eng.score_trace
+
+
+def test_greedy_var_golden(gx, golden):
+    z = golden("greedy_var")
+    for ci in keys(z, "gvar"):
+        name = str(z[f"gvar/{ci}/name"])
+        pool, idx, ref_scores = z[f"gvar/{ci}/pool"], z[f"gvar/{ci}/idx"], z[f"gvar/{ci}/scores"]
+        w = z[f"gvar/{ci}/weights"]
+        w = w if w.size else None
+        seeds = [int(s) for s in z[f"gvar/{ci}/seeds"]]
+        # public API: returns points, mutates the seed list in place (experimentalDesign.py:808,845)
+        keep = list(seeds)
+        pts = gx.ed.performGreedyVarExperimentalDesign(product_kernel(name), pool, len(idx), pool.shape[1], weights=w,
+                                                       indKeepStart=keep)
+        assert np.array_equal(pts, pool[idx]), (ci, name)
+        if seeds:
+            assert keep == [int(i) for i in idx]
+        got_idx, trace = _trace_var(gx, name, pool, len(idx), w, seeds)
+        assert [int(i) for i in got_idx] == [int(i) for i in idx]
+        for s, sc in enumerate(trace):
+            ref = ref_scores[len(seeds) + s]
+            # 1e-9 of the score scale: entries at already-selected points are +-1e-16 round-off in the reference
+            assert np.max(np.abs(sc - ref)) <= 1e-9 * np.max(np.abs(ref)), (ci, s)
+
+
+def test_greedy_ivar_golden(gx, golden):
+    z = golden("greedy_ivar")
+    for ci in keys(z, "givar"):
+        name = str(z[f"givar/{ci}/name"])
+        k = product_kernel(name)
+        cand, mc, noise = z[f"givar/{ci}/cand"], z[f"givar/{ci}/mc"], float(z[f"givar/{ci}/noise"])
+        idx, ref_costs = z[f"givar/{ci}/idx"], z[f"givar/{ci}/costs"]
+        space = gx.Space(k.dimension, None, None, noise=None)
+        cf = gx.ed.costFunctionGP_IVAR(gx.gp.GP(k, noise), 1, space, mcPoints=mc)
+        pts = gx.ed.performGreedyIVARExperimentalDesign(cf, cand, len(idx))
+        assert [int(i) for i in cf.lastIndices] == [int(i) for i in idx], (ci, name)
+        assert np.array_equal(pts, cand[idx])
+        # per-step cost vectors
+        fam, d, params = k._gpx_spec()
+        eng = gx.engine.GreedyIVAREngine(gx.dev, gx.dev.points(cand), gx.dev.points(mc), len(idx), noise,
+                                         gx.engine.prior_scale(fam, params))
+        eng.score_trace = []
+        eng.run(len(idx))
+        for s, c in enumerate(eng.score_trace):
+            err = np.max(np.abs(c - ref_costs[s]) / np.abs(ref_costs[s]))
+            assert err <= 1e-9, (ci, name, s, err)   # north-star tolerance
+        # stateless scoring from host buffers reproduces the same step
+        costs, best = gx.ed.scoreCandidatesIVAR(cf, cand[idx[:3]], cand)
+        assert best == int(idx[3])
+        assert np.max(np.abs(costs - ref_costs[3]) / np.abs(ref_costs[3])) <= 1e-9
+
+
+def test_greedy_mi_golden(gx, golden):
+    z = golden("greedy_mi")
+    for ci in keys(z, "gmi"):
+        name = str(z[f"gmi/{ci}/name"])
+        k = product_kernel(name)
+        pool, noise, start = z[f"gmi/{ci}/pool"], float(z[f"gmi/{ci}/noise"]), int(z[f"gmi/{ci}/start"])
+        idx, ref_scores = z[f"gmi/{ci}/idx"], z[f"gmi/{ci}/scores"]
+        space = gx.Space(k.dimension, None, None, noise=None)
+        cf = gx.ed.costFunctionGP_MI(gx.gp.GP(k, noise), len(idx), space, nmc=len(pool), mcpoints=pool)
+        pts = gx.ed.performGreedyMIExperimentalDesign(cf, len(idx), start=start)
+        assert [int(i) for i in cf.lastIndices] == [int(i) for i in idx], (ci, name)
+        assert np.array_equal(pts, pool[idx])
+        eng = cf._new_engine(len(idx))
+        eng.score_trace = []
+        eng.run(len(idx), start=start)
+        for s, sc in enumerate(eng.score_trace):
+            ref = ref_scores[s + 1]
+            ok = np.isfinite(ref)
+            assert np.array_equal(ok, np.isfinite(sc))
+            err = np.max(np.abs(sc[ok] - ref[ok]) / np.abs(ref[ok]))
+            # the reference's own 1/P_yy - noise cancellation + pinv round-off: 2e-8
+            assert err <= 2e-8, (ci, s, err)
+        # single-candidate API, shape (1,) like the reference
+        j = int(np.flatnonzero(np.isfinite(ref_scores[2]))[3])
+        one = cf.evaluate(j, [int(i) for i in idx[:2]])
+        assert one.shape == (1,)
+        assert abs(one[0] - ref_scores[2][j]) <= 2e-8 * abs(ref_scores[2][j])
+        np.testing.assert_allclose(cf.cov, z[f"gmi/{ci}/cov"], rtol=1e-13)
+
+
+# ------------------------------------------------------------------------------------------------
+# linear algebra building blocks against numpy / scipy
+# ------------------------------------------------------------------------------------------------
+def _spd(rng, n):
+    a = rng.standard_normal((n, n + 5))
+    return a @ a.T / (n + 5) + 0.5 * np.eye(n)
+
+
+@pytest.mark.parametrize("n", [1, 5, 32, 45, 128, 129, 300, 515])
+def test_potrf_trsm_blocks(gx, n):
+    from scipy.linalg import solve_triangular
+    rng = np.random.default_rng(n)
+    dev, lib, ptr = gx.dev, gx.lib, gx.ptr
+    A = _spd(rng, n)
+    ld = gx.device.roundup(n)
+    Ad = dev.zeros(n, ld)
+    Ad[:, :n] = dev.upload(A)
+    info = dev.zeros(1, dtype=gx.torch.int32)
+    gx.check(lib.gpx_potrf(dev.h, ptr(Ad), n, ld, ptr(info), dev.stream))
+    assert int(info.item()) == 0
+    U = np.triu(Ad[:, :n].cpu().numpy())
+    Uref = np.linalg.cholesky(A).T
+    np.testing.assert_allclose(U, Uref, rtol=1e-11, atol=1e-12)
+    # forward solve with a materialised right-hand side, ragged column count
+    m = 77
+    B = rng.standard_normal((n, m))
+    ldb = gx.device.roundup(m)
+    Bd = dev.zeros(n, ldb)
+    Bd[:, :m] = dev.upload(B)
+    gx.check(lib.gpx_trsm(dev.h, ptr(Ad), n, ld, ptr(Bd), m, ldb, dev.stream))
+    X = solve_triangular(Uref, B, trans='T', lower=False)
+    np.testing.assert_allclose(Bd[:, :m].cpu().numpy(), X, rtol=1e-9, atol=1e-10)
+    # back solve needs U^T
+    Ut = dev.zeros(n, ld)
+    gx.check(lib.gpx_transpose(dev.h, ptr(Ad), n, n, ld, ptr(Ut), ld, dev.stream))
+    gx.check(lib.gpx_trsm_back(dev.h, ptr(Ut), n, ld, ptr(Bd), m, ldb, dev.stream))
+    np.testing.assert_allclose(Bd[:, :m].cpu().numpy(), np.linalg.solve(A, B), rtol=1e-8, atol=1e-9)
+    # explicit U^-T, lower triangular with exact zeros above the diagonal
+    Y = dev.zeros(n, ld)
+    gx.check(lib.gpx_trtri_t(dev.h, ptr(Ad), n, ld, ptr(Y), ld, dev.stream))
+    Yh = Y[:, :n].cpu().numpy()
+    assert np.all(np.triu(Yh, 1) == 0.0)
+    np.testing.assert_allclose(Yh, np.linalg.inv(Uref).T, rtol=1e-8, atol=1e-9)
+    # a column of the precision from Y
+    p = dev.upload(np.array([n // 2], dtype=np.int64), dtype=gx.torch.int64)
+    col = dev.zeros(ld)
+    gx.check(lib.gpx_mi_prec_column(dev.h, ptr(Y), n, ld, ptr(p), ptr(col), dev.stream))
+    np.testing.assert_allclose(col[:n].cpu().numpy(), np.linalg.inv(A)[:, n // 2], rtol=1e-7, atol=1e-9)
+    # rank-1 append reproduces the factor of the bordered matrix
+    if n >= 2:
+        Ud = dev.zeros(n, ld)
+        Ud[: n - 1, : n - 1] = dev.upload(np.linalg.cholesky(A[: n - 1, : n - 1]).T.copy())
+        knew = dev.upload(A[: n - 1, n - 1].copy())
+        gx.check(lib.gpx_chol_append(dev.h, ptr(Ud), n - 1, ld, ptr(knew), float(A[n - 1, n - 1]), ptr(info), dev.stream))
+        assert int(info.item()) == 0
+        np.testing.assert_allclose(np.triu(Ud[:, :n].cpu().numpy()), Uref, rtol=1e-10, atol=1e-11)
+
+
+def test_potrf_reports_failing_pivot(gx):
+    dev, lib, ptr = gx.dev, gx.lib, gx.ptr
+    n, ld = 200, 256
+    A = np.eye(n)
+    A[150, 150] = -1.0
+    Ad = dev.zeros(n, ld)
+    Ad[:, :n] = dev.upload(A)
+    info = dev.zeros(1, dtype=gx.torch.int32)
+    gx.check(lib.gpx_potrf(dev.h, ptr(Ad), n, ld, ptr(info), dev.stream))
+    assert int(info.item()) == 151
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (3, 130, 5), (129, 257, 33), (260, 131, 200), (128, 128, 16)])
+def test_dgemm_tn_sub(gx, shape):
+    I, J, K = shape
+    rng = np.random.default_rng(I * 1000 + J)
+    dev, lib, ptr = gx.dev, gx.lib, gx.ptr
+    A, B, Cm = rng.standard_normal((K, I)), rng.standard_normal((K, J)), rng.standard_normal((I, J))
+    lda, ldb, ldc = gx.device.roundup(I), gx.device.roundup(J), gx.device.roundup(J)
+    Ad, Bd, Cd = dev.zeros(K, lda), dev.zeros(K, ldb), dev.zeros(I, ldc)
+    Ad[:, :I], Bd[:, :J], Cd[:, :J] = dev.upload(A), dev.upload(B), dev.upload(Cm)
+    gx.check(lib.gpx_dgemm_tn_sub(dev.h, ptr(Ad), lda, ptr(Bd), ldb, ptr(Cd), ldc, I, J, K, 0, dev.stream))
+    np.testing.assert_allclose(Cd[:, :J].cpu().numpy(), Cm - A.T @ B, rtol=1e-12, atol=1e-12)
+    assert np.all(Cd[:, J:].cpu().numpy() == 0.0)  # padding untouched
+
+
+def test_argreduce_and_sum(gx):
+    dev, lib, ptr, torch = gx.dev, gx.lib, gx.ptr, gx.torch
+    rng = np.random.default_rng(7)
+    best, idx, tot = dev.zeros(1), dev.zeros(1, dtype=torch.int64), dev.zeros(1)
+    for n in [1, 2, 255, 256, 1025, 70001, 3_000_000]:
+        v = rng.standard_normal(n)
+        # plant exact ties at the extremes: numpy returns the first
+        if n > 10:
+            v[[n // 3, n // 2, n - 1]] = v.max() + 1.0
+            v[[n // 5, n // 4]] = v.min() - 1.0
+        vd = dev.upload(v)
+        gx.check(lib.gpx_argreduce(dev.h, ptr(vd), None, None, n, 0, ptr(best), ptr(idx), dev.stream))
+        assert int(idx.item()) == int(np.argmax(v)) and best.item() == v.max()
+        gx.check(lib.gpx_argreduce(dev.h, ptr(vd), None, None, n, 1, ptr(best), ptr(idx), dev.stream))
+        assert int(idx.item()) == int(np.argmin(v)) and best.item() == v.min()
+        w = rng.uniform(0.5, 1.5, n)
+        mask = (rng.uniform(size=n) < 0.3).astype(np.uint8)
+        if mask.all():
+            mask[0] = 0
+        gx.check(lib.gpx_argreduce(dev.h, ptr(vd), ptr(dev.upload(w)), ptr(dev.upload(mask, dtype=torch.uint8)), n, 0,
+                                   ptr(best), ptr(idx), dev.stream))
+        s = np.where(mask == 0, v * w, -np.inf)
+        assert int(idx.item()) == int(np.argmax(s))
+        gx.check(lib.gpx_sum(dev.h, ptr(vd), n, ptr(tot), dev.stream))
+        first = tot.item()
+        assert abs(first - v.sum()) <= 1e-12 * np.abs(v).sum()
+        gx.check(lib.gpx_sum(dev.h, ptr(vd), n, ptr(tot), dev.stream))
+        assert tot.item() == first  # deterministic
+    allmask = dev.upload(np.ones(5, dtype=np.uint8), dtype=torch.uint8)
+    gx.check(lib.gpx_argreduce(dev.h, ptr(dev.zeros(5)), None, ptr(allmask), 5, 0, ptr(best), ptr(idx), dev.stream))
+    assert int(idx.item()) == -1
+
+
+# ------------------------------------------------------------------------------------------------
+# mid-size parity against the CPU oracle (sizes the reference itself cannot reach)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,noise,C,M,n", [("se_ard_2d", 1e-6, 3001, 5003, 130), ("matern_5d", 1e-4, 1500, 2100, 67),
+                                              ("mehler_3d", 1e-2, 1000, 1300, 40), ("se_ard_10d", 1e-6, 2000, 2500, 257),
+                                              ("se_iso_1d", 1e-6, 129, 1, 3), ("se_ard_2d_wide", 1e-6, 1, 300, 5)])
+def test_ivar_scores_vs_oracle(gx, name, noise, C, M, n):
+    rng = np.random.default_rng(C + M)
+    ks = spec(name)
+    k = product_kernel(name)
+    samp = rng.standard_normal if name.startswith("mehler") else (lambda s: rng.uniform(-1, 1, s))
+    cand, mc, design = samp((C, ks.dim)), samp((M, ks.dim)), samp((n, ks.dim))
+    w_m, var_m = orc.fast_design_state(ks, design, mc, noise)
+    w_c, var_c = orc.fast_design_state(ks, design, cand, noise)
+    ref = orc.fast_ivar_scores(ks, cand, mc, w_m, var_m, w_c, var_c, noise)
+    space = gx.Space(ks.dim, None, None, noise=None)
+    cf = gx.ed.costFunctionGP_IVAR(gx.gp.GP(k, noise), 1, space, mcPoints=mc)
+    costs, best = gx.ed.scoreCandidatesIVAR(cf, design, cand)
+    assert best == int(np.argmin(ref))
+    assert np.max(np.abs(costs - ref) / np.abs(ref)) <= 1e-9
+    # and the reference-shaped single evaluation agrees with the batched score
+    one = gx.ed.costFunctionGP_IVAR(gx.gp.GP(k, noise), n + 1, space, mcPoints=mc).evaluate(np.vstack([design, cand[:1]]))
+    assert abs(one - ref[0]) <= 1e-9 * abs(ref[0])
+
+
+def test_ivar_empty_design_and_duplicates(gx):
+    rng = np.random.default_rng(11)
+    ks, k = spec("se_ard_2d_wide"), product_kernel("se_ard_2d_wide")
+    cand, mc = rng.uniform(-1, 1, (300, 2)), rng.uniform(-1, 1, (900, 2))
+    cand[17] = cand[5]  # duplicate candidates, noise 0: pinv 'no reduction' rule once one of them is chosen
+    fidx, fcosts = orc.fast_greedy_ivar(ks, cand, mc, 8, 0.0)
+    space = gx.Space(2, None, None, noise=None)
+    cf = gx.ed.costFunctionGP_IVAR(gx.gp.GP(k, 0.0), 1, space, mcPoints=mc)
+    idx = gx.ed.performGreedyIVARExperimentalDesign(cf, cand, 8, returnIndices=True)
+    assert [int(i) for i in idx] == fidx
+    costs0, best0 = gx.ed.scoreCandidatesIVAR(cf, cand[:0], cand)
+    assert best0 == fidx[0]
+    assert np.max(np.abs(costs0 - fcosts[0]) / np.abs(fcosts[0])) <= 1e-9
+
+
+def test_greedy_var_mid_vs_oracle(gx):
+    rng = np.random.default_rng(3)
+    for name, C, N in [("matern_5d", 20011, 150), ("se_ard_10d", 5000, 140)]:
+        ks = spec(name)
+        pool = rng.uniform(-1, 1, (C, ks.dim))
+        fidx, fscores = orc.fast_greedy_var(ks, pool, N)
+        idx, trace = _trace_var(gx, name, pool, N, None, [])
+        assert [int(i) for i in idx] == fidx, name
+        for s in (0, 1, N // 2, N - 1):
+            assert np.max(np.abs(trace[s] - fscores[s])) <= 1e-9 * np.max(np.abs(fscores[s]))
+
+
+def test_greedy_var_factor_property(gx):
+    """Size-independent property at a large pool: the appended rows restricted to the picks are the
+    Cholesky factor of K(picks, picks), and every running variance equals prior - colsumsq(W)."""
+    rng = np.random.default_rng(5)
+    name, C, N = "matern_5d", 250_000, 96
+    ks = spec(name)
+    pool = rng.uniform(-1, 1, (C, 5))
+    bind(gx, name)
+    eng = gx.engine.GreedyVarEngine(gx.dev, gx.dev.points(pool), N)
+    idx = eng.run(N)
+    assert len(set(int(i) for i in idx)) == N
+    L = eng.W[:N][:, gx.torch.as_tensor(idx, device=eng.W.device)].cpu().numpy().T
+    assert np.allclose(np.triu(L, 1), 0.0, atol=1e-9) and np.all(np.diag(L) > 0)
+    Kpp = ks.gram(pool[idx], pool[idx])
+    np.testing.assert_allclose(L @ L.T, Kpp, rtol=1e-10, atol=1e-10)
+    chk = rng.integers(0, C, 200)
+    Wc = eng.W[:N][:, gx.torch.as_tensor(chk, device=eng.W.device)].cpu().numpy()
+    var = eng.var.cpu().numpy()[chk]
+    np.testing.assert_allclose(var, ks.prior(pool[chk]) - np.sum(Wc * Wc, axis=0), rtol=1e-9, atol=1e-11)
+    # greedy property: scores of successive picks never increase
+    sc = eng.pick_scores[:N].cpu().numpy()
+    assert np.all(np.diff(sc) <= 1e-12)
+
+
+def test_greedy_mi_mid_vs_oracle(gx):
+    rng = np.random.default_rng(9)
+    ks, k = spec("mehler_3d"), product_kernel("mehler_3d")
+    pool = rng.standard_normal((700, 3))
+    fidx, fscores = orc.fast_greedy_mi(ks, pool, 1e-2, 12, start=3)
+    space = gx.Space(3, None, None, noise=None)
+    cf = gx.ed.costFunctionGP_MI(gx.gp.GP(k, 1e-2), 12, space, nmc=700, mcpoints=pool)
+    gx.ed.performGreedyMIExperimentalDesign(cf, 12, start=3)
+    assert [int(i) for i in cf.lastIndices] == fidx
+
+
+def test_posterior_variance_large_vs_oracle(gx):
+    rng = np.random.default_rng(13)
+    name = "se_ard_10d"
+    ks, k = spec(name), product_kernel(name)
+    nodes, query = rng.uniform(-1, 1, (600, 10)), rng.uniform(-1, 1, (10_007, 10))
+    g = gx.gp.GP(k, 1e-6)
+    g.addNodesAndComputeCovariance(nodes)
+    var = g.evaluateVariance(query)
+    ref = orc.fast_posterior_variance(ks, nodes, query, 1e-6)
+    assert np.max(np.abs(var - ref)) <= 1e-9 * np.max(ks.prior(query))
