@@ -291,6 +291,15 @@ class GreedyIVAREngine(_Pivoting):
         self._force_local(int(global_index))
         self.append()
 
+    def snapshot(self):
+        """Cheap save point (running variances + design size); rows >= n of W are never read."""
+        return (self.n, self.varC.clone(), self.varM.clone())
+
+    def restore(self, snap):
+        self.n = snap[0]
+        self.varC.copy_(snap[1])
+        self.varM.copy_(snap[2])
+
     def rollback(self, n_keep: int):
         """Forget the rows appended after n_keep (bench.py re-times the same step)."""
         assert 0 <= n_keep <= self.n
