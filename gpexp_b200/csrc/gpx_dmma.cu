@@ -17,22 +17,39 @@
 //   j_local = wn*64 + (u>>1)*16 + (lane>>2)*2 + (u&1)            u = 0..7  (B fragments, load side)
 //   accumulator (t,u,e) sits at column  wn*64 + (u>>1)*16 + ((lane&3)*2+e)*2 + (u&1)
 #include <math.h>
+#include <stdlib.h>
 
 #include "gpx_common.cuh"
 
+#ifndef GPX_DEFAULT_WM
+#define GPX_DEFAULT_WM 2
+#endif
+
 namespace {
 
-constexpr int BM = 128;
 constexpr int BN = 128;
 constexpr int BK = 16;
 constexpr int STAGES = 4;
-constexpr int NTHREADS = 256;
-constexpr int LDSM = 132;                       // padded row stride (doubles)
-constexpr int STAGE_DOUBLES = 2 * BK * LDSM;    // A rows then B rows
-constexpr int SMEM_DOUBLES = STAGES * STAGE_DOUBLES + BM + BN + 4 * BN;
-constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES * sizeof(double);
 
 enum { EPI_IVAR = 0, EPI_STORE = 1, EPI_SUB = 2 };
+
+// WM = warps along i.  WM=4: 256 threads, 128x128 tile, 1 CTA/SM.  WM=2: 128 threads, 64x128 tile, 2 CTAs/SM
+// (two independent CTAs de-phase the barriers and the exp prologue against each other's DMMA stream).
+template <int WM>
+struct Cfg {
+    static constexpr int NT = WM * 64;
+    static constexpr int BM = WM * 32;
+    static constexpr int LDA = BM + 4;  // row strides = 4 (mod 16) doubles: conflict-free LDS.128 fragment loads
+    static constexpr int LDB = BN + 4;
+    static constexpr int STAGE = BK * (LDA + LDB);
+    static constexpr int PIECES_A = BK * BM / 2;  // 16-byte pieces per chunk
+    static constexpr int PIECES = BK * (BM + BN) / 2;
+    static constexpr int PER_THREAD = PIECES / NT;
+    static constexpr int A_ITERS = PIECES_A / NT;
+    static constexpr int SMEM_DOUBLES = STAGES * STAGE + 2 * BM + BN + WM * BN;
+    static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES * sizeof(double);
+    static_assert(PIECES % NT == 0 && PIECES_A % NT == 0, "loader mapping");
+};
 
 struct CoreArgs {
     const double* A;   // K x I (main operand)
@@ -67,17 +84,42 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-template <int FAM, int EPI, bool PRO>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int LDA_, int LDB_>
+__device__ __forceinline__ void load_frags(double (&af)[4], double (&bf)[8], const double* pa, const double* pb, int ks) {
+#pragma unroll
+    for (int t2 = 0; t2 < 2; ++t2) {
+        const double2 v = *reinterpret_cast<const double2*>(pa + ks * 4 * LDA_ + t2 * 16);
+        af[t2 * 2] = v.x;
+        af[t2 * 2 + 1] = v.y;
+    }
+#pragma unroll
+    for (int u2 = 0; u2 < 4; ++u2) {
+        const double2 v = *reinterpret_cast<const double2*>(pb + ks * 4 * LDB_ + u2 * 16);
+        bf[u2 * 2] = v.x;
+        bf[u2 * 2 + 1] = v.y;
+    }
+}
+
+__device__ __forceinline__ void mma_tile(double (&acc)[4][8][2], const double (&af)[4], const double (&bf)[8]) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dmma(acc[t][u][0], acc[t][u][1], af[t], bf[u]);
+}
+
+template <int FAM, int EPI, bool PRO, int WM>
+__global__ void __launch_bounds__(WM * 64, WM == 4 ? 1 : 2)
     dmma_core_kernel(const __grid_constant__ CoreArgs a, const __grid_constant__ KParams kp) {
+    using C = Cfg<WM>;
+    constexpr int BM = C::BM, NT = C::NT, LDA = C::LDA, LDB = C::LDB;
     extern __shared__ __align__(16) double smem[];
-    double* s_alpha = smem + STAGES * STAGE_DOUBLES;
-    double* s_beta = s_alpha + BM;
+    double* s_alpha = smem + STAGES * C::STAGE;  // [2][BM], by tile parity
+    double* s_beta = s_alpha + 2 * BM;
     double* s_red = s_beta + BN;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int wm = warp & 3, wn = warp >> 2;
+    const int wm = warp % WM, wn = warp / WM;
     const int g4 = lane >> 2, q4 = lane & 3;
 
     const int64_t j0 = (int64_t)blockIdx.x * BN;
@@ -95,110 +137,132 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     }
     const int ntiles = it_end > it_begin ? (int)(it_end - it_begin) : 0;
     const int kch = (a.K + BK - 1) / BK;
-    const int T = (PRO ? 1 : 0) + kch;   // chunks per tile
+    const int T = (PRO ? 1 : 0) + kch;  // chunks per tile
     const int G = ntiles * T;
 
-    // ---- chunk loader: 2048 16-byte pieces per chunk, 8 per thread ---------------------------------
-    auto issue = [&](int g) {
-        if (g < G) {
-            const int tl = g / T;
-            const int ch = g - tl * T;
-            const int64_t i0 = (it_begin + tl) * BM;
+    // ---- chunk loader (cp.async ring, 3 chunks in flight) ------------------------------------------
+    int is_g = 0, is_tl = 0, is_ch = 0;
+    auto issue = [&]() {
+        if (is_g < G) {
+            const int64_t i0 = (it_begin + is_tl) * BM;
             const double *srcA, *srcB;
             int krows;
-            if (PRO && ch == 0) {
+            if (PRO && is_ch == 0) {
                 srcA = a.Ap;
                 srcB = a.Bp;
                 krows = a.dpad;
             } else {
-                const int kc = ch - (PRO ? 1 : 0);
+                const int kc = is_ch - (PRO ? 1 : 0);
                 srcA = a.A + (int64_t)kc * BK * a.lda;
                 srcB = a.B + (int64_t)kc * BK * a.ldb;
                 krows = a.K - kc * BK;
             }
-            double* sA = smem + (g % STAGES) * STAGE_DOUBLES;
+            double* sA = smem + (is_g % STAGES) * C::STAGE;
+            double* sB = sA + BK * LDA;
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int p = tid + it * NTHREADS;
-                const int mat = p >> 10;
-                const int row = (p >> 6) & 15;
-                const int c2 = (p & 63) * 2;
-                const double* base = mat ? srcB : srcA;
-                const int64_t ld = mat ? a.ldb : a.lda;
-                const int64_t col = (mat ? j0 : i0) + c2;
-                const bool ok = (row < krows) && (col < (mat ? a.J : a.I));
-                cp_async16(sA + mat * (BK * LDSM) + row * LDSM + c2, ok ? base + (int64_t)row * ld + col : base, ok);
+            for (int it = 0; it < C::PER_THREAD; ++it) {
+                if (it < C::A_ITERS) {
+                    const int p = tid + it * NT;
+                    const int row = p / (BM / 2), c2 = (p % (BM / 2)) * 2;
+                    const bool ok = (row < krows) && (i0 + c2 < a.I);
+                    cp_async16(sA + row * LDA + c2, ok ? srcA + (int64_t)row * a.lda + i0 + c2 : srcA, ok);
+                } else {
+                    const int p = tid + it * NT - C::PIECES_A;
+                    const int row = p / (BN / 2), c2 = (p % (BN / 2)) * 2;
+                    const bool ok = (row < krows) && (j0 + c2 < a.J);
+                    cp_async16(sB + row * LDB + c2, ok ? srcB + (int64_t)row * a.ldb + j0 + c2 : srcB, ok);
+                }
+            }
+            if (++is_ch == T) {
+                is_ch = 0;
+                ++is_tl;
             }
         }
+        ++is_g;
         cp_async_commit();
+    };
+    // chunk g+1 landed and visible to all warps; the stage of chunk g-1 is free -> refill it with chunk g+3
+    auto midsync = [&]() {
+        cp_async_wait<1>();
+        __syncthreads();
+        issue();
     };
 
     double acc[4][8][2];
-    double rs[8][2];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) rs[u][0] = rs[u][1] = 0.0;
+    double rs[2] = {0.0, 0.0};
+    double af0[4], bf0[8], af1[4], bf1[8];
 
     if (PRO) {
         if (tid < BN) s_beta[tid] = (j0 + tid < a.J) ? a.Bs[j0 + tid] : 0.0;
     }
 
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) issue(s);
+    issue();
+    issue();
+    issue();
+    cp_async_wait<2>();
+    __syncthreads();
 
+    const int fa = q4 * LDA + wm * 32 + g4 * 2;  // fragment offsets inside a stage
+    const int fb = q4 * LDB + wn * 64 + g4 * 2;
     int tl = 0, ch = 0;
+    bool pre = false;
     for (int g = 0; g < G; ++g) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        issue(g + STAGES - 1);
-
         const int64_t i0 = (it_begin + tl) * BM;
         if (ch == 0) {
 #pragma unroll
             for (int t = 0; t < 4; ++t)
 #pragma unroll
                 for (int u = 0; u < 8; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
-            if (PRO && tid < BM) s_alpha[tid] = (i0 + tid < a.I) ? a.As[i0 + tid] : 0.0;
+            if (PRO && tid < BM) s_alpha[(tl & 1) * BM + tid] = (i0 + tid < a.I) ? a.As[i0 + tid] : 0.0;
         }
-
-        const double* sA = smem + (g % STAGES) * STAGE_DOUBLES;
-        const double* sB = sA + BK * LDSM;
+        const double* pa = smem + (g % STAGES) * C::STAGE + fa;
+        const double* pb = smem + (g % STAGES) * C::STAGE + BK * LDA + fb;
         int ksteps;
-        if (PRO && ch == 0) {
-            ksteps = a.dpad >> 2;
-        } else {
+        bool next_full;
+        {
             const int kc = ch - (PRO ? 1 : 0);
-            const int rem = a.K - kc * BK;
-            ksteps = rem >= BK ? 4 : ((rem + 3) >> 2);
+            if (PRO && ch == 0) {
+                ksteps = a.dpad >> 2;
+            } else {
+                const int rem = a.K - kc * BK;
+                ksteps = rem >= BK ? 4 : ((rem + 3) >> 2);
+            }
+            next_full = (a.K - (kc + 1) * BK) >= BK;
         }
-        const double* pa = sA + q4 * LDSM + wm * 32 + g4 * 2;
-        const double* pb = sB + q4 * LDSM + wn * 64 + g4 * 2;
+        if (ksteps == 4) {
+            // software-pipelined: fragments of k-step s+1 are fetched while the DMMAs of k-step s issue
+            if (!pre) load_frags<LDA, LDB>(af0, bf0, pa, pb, 0);
+            load_frags<LDA, LDB>(af1, bf1, pa, pb, 1);
+            mma_tile(acc, af0, bf0);
+            load_frags<LDA, LDB>(af0, bf0, pa, pb, 2);
+            mma_tile(acc, af1, bf1);
+            load_frags<LDA, LDB>(af1, bf1, pa, pb, 3);
+            mma_tile(acc, af0, bf0);
+            midsync();
+            const bool np = (ch + 1 < T) && !(PRO && ch == 0) && next_full;
+            if (np) {
+                const double* na = smem + ((g + 1) % STAGES) * C::STAGE + fa;
+                const double* nb = smem + ((g + 1) % STAGES) * C::STAGE + BK * LDA + fb;
+                load_frags<LDA, LDB>(af0, bf0, na, nb, 0);
+            }
+            mma_tile(acc, af1, bf1);
+            pre = np;
+        } else {
 #pragma unroll 1
-        for (int ks = 0; ks < ksteps; ++ks) {
-            double af[4], bf[8];
-#pragma unroll
-            for (int t2 = 0; t2 < 2; ++t2) {
-                const double2 v = *reinterpret_cast<const double2*>(pa + ks * 4 * LDSM + t2 * 16);
-                af[t2 * 2] = v.x;
-                af[t2 * 2 + 1] = v.y;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                if (ks == ksteps - 1) midsync();
+                load_frags<LDA, LDB>(af0, bf0, pa, pb, ks);
+                mma_tile(acc, af0, bf0);
             }
-#pragma unroll
-            for (int u2 = 0; u2 < 4; ++u2) {
-                const double2 v = *reinterpret_cast<const double2*>(pb + ks * 4 * LDSM + u2 * 16);
-                bf[u2 * 2] = v.x;
-                bf[u2 * 2 + 1] = v.y;
-            }
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-#pragma unroll
-                for (int u = 0; u < 8; ++u) dmma(acc[t][u][0], acc[t][u][1], af[t], bf[u]);
+            pre = false;
         }
 
         if (PRO && ch == 0) {
             // covariance from the expanded form; accumulators become -k so that the main loop yields T - k
-            __syncthreads();  // s_alpha (and, first time, s_beta) visible
+            const double* sal = s_alpha + (tl & 1) * BM;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const double al = s_alpha[wm * 32 + (t >> 1) * 16 + g4 * 2 + (t & 1)];
+                const double al = sal[wm * 32 + (t >> 1) * 16 + g4 * 2 + (t & 1)];
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
 #pragma unroll
@@ -213,6 +277,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             // ---- tile epilogue ---------------------------------------------------------------------
             if (EPI == EPI_IVAR) {
                 const bool full = (i0 + BM <= a.I);
+                double p[8][2];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) p[u][0] = p[u][1] = 0.0;
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const int64_t i = i0 + wm * 32 + (t >> 1) * 16 + g4 * 2 + (t & 1);
@@ -222,8 +289,33 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const double v = ok ? acc[t][u][e] : 0.0;
-                            rs[u][e] = fma(v, v, rs[u][e]);
+                            p[u][e] = fma(v, v, p[u][e]);
                         }
+                }
+                // butterfly reduce-scatter over the 8 lanes that share q4: lane g4 ends up owning u = g4
+                const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+                double h[4][2], q[2][2];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const double keep = b4 ? p[u + 4][e] : p[u][e];
+                        const double send = b4 ? p[u][e] : p[u + 4][e];
+                        h[u][e] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const double keep = b3 ? h[u + 2][e] : h[u][e];
+                        const double send = b3 ? h[u][e] : h[u + 2][e];
+                        q[u][e] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double keep = b2 ? q[1][e] : q[0][e];
+                    const double send = b2 ? q[0][e] : q[1][e];
+                    rs[e] += keep + __shfl_xor_sync(0xffffffffu, send, 4);
                 }
             } else {
 #pragma unroll
@@ -266,48 +358,353 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     cp_async_wait<0>();
 
     if (EPI == EPI_IVAR) {
-        // reduce the per-thread partial sums over the 8 lanes that share a column, then over the 4 i-warps
+        // lane (g4,q4) owns columns u = g4, e = 0,1 of its warp; add the WM i-warps in a fixed order
+        __syncthreads();
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int e = 0; e < 2; ++e) s_red[wm * BN + wn * 64 + (g4 >> 1) * 16 + (q4 * 2 + e) * 2 + (g4 & 1)] = rs[e];
+        __syncthreads();
+        for (int c = tid; c < BN; c += NT) {
+            if (j0 + c < a.J) {
+                double r = s_red[c];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                double v = rs[u][e];
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                v += __shfl_xor_sync(0xffffffffu, v, 8);
-                v += __shfl_xor_sync(0xffffffffu, v, 16);
-                rs[u][e] = v;
+                for (int w = 1; w < WM; ++w) r += s_red[w * BN + c];
+                a.out[(int64_t)blockIdx.y * a.ldo + j0 + c] = r;
             }
-        __syncthreads();
-        if (g4 == 0) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-#pragma unroll
-                for (int e = 0; e < 2; ++e)
-                    s_red[wm * BN + wn * 64 + (u >> 1) * 16 + (q4 * 2 + e) * 2 + (u & 1)] = rs[u][e];
-        }
-        __syncthreads();
-        if (tid < BN && j0 + tid < a.J) {
-            const double r = ((s_red[tid] + s_red[BN + tid]) + s_red[2 * BN + tid]) + s_red[3 * BN + tid];
-            a.out[(int64_t)blockIdx.y * a.ldo + j0 + tid] = r;
         }
     }
 }
 
-template <int FAM, int EPI, bool PRO>
-int launch_core(const CoreArgs& a, const KParams& kp, dim3 grid, cudaStream_t st) {
+// ---------------------------------------------------------------------------------------------
+// TMA + mbarrier IVAR contraction (the hot kernel): operand chunks arrive by TMA bulk copies
+// (cp.async.bulk -> UBLKCP) that complete on mbarriers; the eight warps do LDS.128 + DMMA and take turns
+// (warp g mod 8 for chunk g+3) at issuing the 33 bulk copies of a chunk -- a ninth, dedicated producer warp
+// would put three warps on one sub-partition and cap everybody at 168 registers.  No CTA-wide barrier in
+// the main loop, so warps drift apart and one warp's exp prologue / epilogue overlaps the other warp's
+// DMMA stream on the same sub-partition.
+// Requires fully padded operands: lda, ldb multiples of 128 covering whole tiles (the engines guarantee it).
+// ---------------------------------------------------------------------------------------------
+constexpr int WS_CONSUMERS = 8;
+constexpr int WS_THREADS = WS_CONSUMERS * 32;
+constexpr int WS_BM = 128;
+constexpr int WS_LD = 132;
+constexpr int WS_STAGE = BK * 2 * WS_LD;  // doubles
+constexpr int WS_STAGES = 6;               // ring depth
+constexpr int WS_AHEAD = 3;                // chunks in flight; the refilled stage was released 3 chunks ago
+constexpr int WS_SMEM_DOUBLES = WS_STAGES * WS_STAGE + WS_STAGES * WS_BM + BN + 4 * BN + 2 * WS_STAGES;
+constexpr size_t WS_SMEM_BYTES = (size_t)WS_SMEM_DOUBLES * sizeof(double);
+
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned int parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(double* dst, const double* src, unsigned int bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int FAM, bool DB>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+    ivar_ws_kernel(const __grid_constant__ CoreArgs a, const __grid_constant__ KParams kp) {
+    constexpr int BM = WS_BM, LD = WS_LD;
+    extern __shared__ __align__(16) double smem[];
+    double* s_alpha = smem + WS_STAGES * WS_STAGE;  // [WS_STAGES][BM], travels with the prologue chunk
+    double* s_beta = s_alpha + WS_STAGES * BM;
+    double* s_red = s_beta + BN;
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_red + 4 * BN);
+    uint64_t* empty = full + WS_STAGES;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int64_t j0 = (int64_t)blockIdx.x * BN;
+    const int64_t itiles = (a.I + BM - 1) / BM;
+    const int64_t it_begin = (int64_t)blockIdx.y * a.tiles_per_cta;
+    int64_t it_end = it_begin + a.tiles_per_cta;
+    if (it_end > itiles) it_end = itiles;
+    const int ntiles = it_end > it_begin ? (int)(it_end - it_begin) : 0;
+    const int kch = (a.K + BK - 1) / BK;
+    const int T = 1 + kch;
+    const int G = ntiles * T;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < WS_STAGES; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, WS_CONSUMERS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (tid < BN) s_beta[tid] = (j0 + tid < a.J) ? a.Bs[j0 + tid] : 0.0;
+    __syncthreads();
+
+    double rs[2] = {0.0, 0.0};
+    const int wm = warp & 3, wn = (warp >> 2) & 1;
+    const int g4 = lane >> 2, q4 = lane & 3;
+
+    // ---- producer step, executed by one warp per chunk; all addresses are warp-uniform so that the 33 bulk
+    //      copies issue back to back from one lane (UBLKCP takes uniform registers) -----------------------
+    auto produce = [&](int c) {
+        if (c >= G) return;
+        const int s = c % WS_STAGES;
+        const unsigned int ph = (unsigned int)(c / WS_STAGES) & 1u;
+        mbar_wait(empty + s, ph ^ 1u);
+        const int ptl = c / T, pch = c - ptl * T;
+        const int64_t i0 = (it_begin + ptl) * BM;
+        const double *srcA, *srcB;
+        int krows, ksteps;
+        if (pch == 0) {
+            srcA = a.Ap + i0;
+            srcB = a.Bp + j0;
+            krows = a.dpad;
+            ksteps = a.dpad >> 2;
+        } else {
+            const int kc = pch - 1;
+            srcA = a.A + (int64_t)kc * BK * a.lda + i0;
+            srcB = a.B + (int64_t)kc * BK * a.ldb + j0;
+            const int rem = a.K - kc * BK;
+            krows = rem < BK ? rem : BK;
+            ksteps = rem >= BK ? 4 : ((rem + 3) >> 2);
+        }
+        double* stA = smem + s * WS_STAGE;
+        double* stB = stA + BK * LD;
+        if (krows < ksteps * 4) {
+            // K tail: rows the DMMAs will read but the operand does not have -> explicit zeros (lane -> column pair)
+            for (int r = krows; r < ksteps * 4; ++r) {
+                for (int cc = lane * 2; cc < BM; cc += 64) {
+                    *reinterpret_cast<double2*>(stA + r * LD + cc) = make_double2(0.0, 0.0);
+                    *reinterpret_cast<double2*>(stB + r * LD + cc) = make_double2(0.0, 0.0);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic writes before later TMA writes here
+            __syncwarp();
+        }
+        if (lane == 0) {
+            const unsigned int bytes = (unsigned int)krows * (BM + BN) * 8u + (pch == 0 ? BM * 8u : 0u);
+            mbar_arrive_expect_tx(full + s, bytes);
+#pragma unroll 4
+            for (int r = 0; r < krows; ++r) {
+                bulk_g2s(stA + r * LD, srcA + (int64_t)r * a.lda, BM * 8u, full + s);
+                bulk_g2s(stB + r * LD, srcB + (int64_t)r * a.ldb, BN * 8u, full + s);
+            }
+            if (pch == 0) bulk_g2s(s_alpha + s * BM, a.As + i0, BM * 8u, full + s);
+        }
+        __syncwarp();
+    };
+    if (warp < WS_AHEAD) produce(warp);
+
+    {
+        // ================= consumer warps ===========================================================
+        double acc[4][8][2];
+        double af0[4], bf0[8], af1[4], bf1[8];
+        const int fa = q4 * LD + wm * 32 + g4 * 2;
+        const int fb = BK * LD + q4 * LD + wn * 64 + g4 * 2;
+        int tl = 0, ch = 0;
+        for (int g = 0; g < G; ++g) {
+            const int s = g % WS_STAGES;
+            const unsigned int ph = (unsigned int)(g / WS_STAGES) & 1u;
+            const int64_t i0 = (it_begin + tl) * BM;
+            if (warp == (g & (WS_CONSUMERS - 1))) produce(g + WS_AHEAD);
+            if (ch == 0) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
+            }
+            mbar_wait(full + s, ph);
+            const double* pa = smem + s * WS_STAGE + fa;
+            const double* pb = smem + s * WS_STAGE + fb;
+            int ksteps;
+            if (ch == 0) {
+                ksteps = a.dpad >> 2;
+            } else {
+                const int rem = a.K - (ch - 1) * BK;
+                ksteps = rem >= BK ? 4 : ((rem + 3) >> 2);
+            }
+            if (DB && ksteps == 4) {
+                load_frags<LD, LD>(af0, bf0, pa, pb, 0);
+                load_frags<LD, LD>(af1, bf1, pa, pb, 1);
+                mma_tile(acc, af0, bf0);
+                load_frags<LD, LD>(af0, bf0, pa, pb, 2);
+                mma_tile(acc, af1, bf1);
+                load_frags<LD, LD>(af1, bf1, pa, pb, 3);
+                mma_tile(acc, af0, bf0);
+                mma_tile(acc, af1, bf1);
+            } else {
+#pragma unroll 1
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    load_frags<LD, LD>(af0, bf0, pa, pb, ks);
+                    mma_tile(acc, af0, bf0);
+                }
+            }
+            if (ch == 0) {
+                // covariance from the expanded form; accumulators become -k so that the main loop yields T - k
+                const double* sal = s_alpha + s * BM;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const double al = sal[wm * 32 + (t >> 1) * 16 + g4 * 2 + (t & 1)];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const double be = s_beta[wn * 64 + (u >> 1) * 16 + (q4 * 2 + e) * 2 + (u & 1)];
+                            acc[t][u][e] = -kexpand<FAM>(acc[t][u][e] + al + be, kp);
+                        }
+                }
+            }
+            // this warp is done with stage s (all its LDS results have been consumed by issued DMMAs)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + s);
+
+            if (ch == T - 1) {
+                const bool fullt = (i0 + BM <= a.I);
+                double p[8][2];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) p[u][0] = p[u][1] = 0.0;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int64_t i = i0 + wm * 32 + (t >> 1) * 16 + g4 * 2 + (t & 1);
+                    const bool ok = fullt || (i < a.I);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const double v = ok ? acc[t][u][e] : 0.0;
+                            p[u][e] = fma(v, v, p[u][e]);
+                        }
+                }
+                const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+                double h[4][2], q[2][2];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const double keep = b4 ? p[u + 4][e] : p[u][e];
+                        const double send = b4 ? p[u][e] : p[u + 4][e];
+                        h[u][e] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const double keep = b3 ? h[u + 2][e] : h[u][e];
+                        const double send = b3 ? h[u][e] : h[u + 2][e];
+                        q[u][e] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double keep = b2 ? q[1][e] : q[0][e];
+                    const double send = b2 ? q[0][e] : q[1][e];
+                    rs[e] += keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+                ch = 0;
+                ++tl;
+            } else {
+                ++ch;
+            }
+        }
+    }
+
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 2; ++e) s_red[wm * BN + wn * 64 + (g4 >> 1) * 16 + (q4 * 2 + e) * 2 + (g4 & 1)] = rs[e];
+    __syncthreads();
+    if (tid < BN && j0 + tid < a.J) {
+        const double r = ((s_red[tid] + s_red[BN + tid]) + s_red[2 * BN + tid]) + s_red[3 * BN + tid];
+        a.out[(int64_t)blockIdx.y * a.ldo + j0 + tid] = r;
+    }
+}
+
+bool ivar_use_tma() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GPX_IVAR_TMA");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+bool ivar_double_buffer() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GPX_IVAR_DB");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
+template <int FAM, bool DB>
+int launch_ivar_ws_db(const CoreArgs& a, const KParams& kp, dim3 grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(dmma_core_kernel<FAM, EPI, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(ivar_ws_kernel<FAM, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES);
         if (e != cudaSuccess) {
-            gpx_set_error("dmma core: cannot opt in to %zu bytes of shared memory: %s", SMEM_BYTES, cudaGetErrorString(e));
+            gpx_set_error("ivar_ws: cannot opt in to %zu bytes of shared memory: %s", WS_SMEM_BYTES, cudaGetErrorString(e));
             return (int)e;
         }
         configured = true;
     }
-    dmma_core_kernel<FAM, EPI, PRO><<<grid, NTHREADS, SMEM_BYTES, st>>>(a, kp);
+    ivar_ws_kernel<FAM, DB><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(a, kp);
+    return gpx_check_launch("ivar_ws");
+}
+template <int FAM>
+int launch_ivar_ws(const CoreArgs& a, const KParams& kp, dim3 grid, cudaStream_t st) {
+    return ivar_double_buffer() ? launch_ivar_ws_db<FAM, true>(a, kp, grid, st) : launch_ivar_ws_db<FAM, false>(a, kp, grid, st);
+}
+
+// tile shape used by every launch: GPX_WM=2 (64x128, 2 CTAs/SM) or 4 (128x128, 1 CTA/SM)
+int core_wm() {
+    static int wm = 0;
+    if (wm == 0) {
+        const char* e = getenv("GPX_WM");
+        wm = (e && e[0] == '4') ? 4 : ((e && e[0] == '2') ? 2 : GPX_DEFAULT_WM);
+    }
+    return wm;
+}
+
+template <int FAM, int EPI, bool PRO, int WM>
+int launch_core_wm(const CoreArgs& a, const KParams& kp, dim3 grid, cudaStream_t st) {
+    using C = Cfg<WM>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(dmma_core_kernel<FAM, EPI, PRO, WM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)C::SMEM_BYTES);
+        if (e != cudaSuccess) {
+            gpx_set_error("dmma core: cannot opt in to %zu bytes of shared memory: %s", C::SMEM_BYTES, cudaGetErrorString(e));
+            return (int)e;
+        }
+        configured = true;
+    }
+    dmma_core_kernel<FAM, EPI, PRO, WM><<<grid, C::NT, C::SMEM_BYTES, st>>>(a, kp);
     return gpx_check_launch("dmma core");
 }
+
+template <int FAM, int EPI, bool PRO>
+int launch_core(const CoreArgs& a, const KParams& kp, int64_t jt, int64_t it_or_splits, cudaStream_t st) {
+    dim3 grid((unsigned)jt, (unsigned)it_or_splits);
+    if (core_wm() == 4) return launch_core_wm<FAM, EPI, PRO, 4>(a, kp, grid, st);
+    return launch_core_wm<FAM, EPI, PRO, 2>(a, kp, grid, st);
+}
+
+int core_bm() { return core_wm() * 32; }
+int ivar_bm() { return ivar_use_tma() ? WS_BM : core_bm(); }
 
 int check_operand(const double* p, int64_t ld, const char* name) {
     if (!gpx_aligned16(p) || (ld & 1)) {
@@ -322,7 +719,7 @@ int check_operand(const double* p, int64_t ld, const char* name) {
 // number of i-splits for the IVAR grid: fill the machine in whole waves
 int gpx_ivar_splits(gpx_handle h, int64_t M, int64_t C) {
     const int64_t jt = (C + BN - 1) / BN;
-    const int64_t itl = (M + BM - 1) / BM;
+    const int64_t itl = (M + ivar_bm() - 1) / ivar_bm();
     const int sms = h->sm_count > 0 ? h->sm_count : 148;
     int best = 1;
     double best_eff = -1.0;
@@ -353,7 +750,7 @@ int gpx_launch_core_ivar(gpx_handle h, const double* Wm, int64_t ldm, const doub
         if ((rc = check_operand(Wc, ldc, "Wc"))) return rc;
     }
     const int splits = gpx_ivar_splits(h, M, C);
-    const int64_t itl = (M + BM - 1) / BM;
+    const int64_t itl = (M + ivar_bm() - 1) / ivar_bm();
     CoreArgs a;
     a.A = Wm;
     a.B = Wc;
@@ -371,9 +768,20 @@ int gpx_launch_core_ivar(gpx_handle h, const double* Wm, int64_t ldm, const doub
     a.dpad = (h->kp.d + 3) & ~3;
     a.tiles_per_cta = (int)((itl + splits - 1) / splits);
     a.upper_only = 0;
-    dim3 grid((unsigned)((C + BN - 1) / BN), (unsigned)splits);
     *nsplit_out = splits;
-    GPX_DISPATCH_FAMILY(h->kp.family, rc = (launch_core<FAM, EPI_IVAR, true>(a, h->kp, grid, st)));
+    // the TMA path reads whole 128-wide tiles: operands must be padded to full tiles
+    const bool padded = (ldm % WS_BM) == 0 && (ldc % BN) == 0 && ldm >= (M + WS_BM - 1) / WS_BM * WS_BM &&
+                        ldc >= (C + BN - 1) / BN * BN;
+    if (ivar_use_tma()) {
+        if (!padded) {
+            gpx_set_error("gpx_score_ivar: leading dimensions must be multiples of 128 covering whole tiles");
+            return GPX_EALIGN;
+        }
+        dim3 grid((unsigned)((C + BN - 1) / BN), (unsigned)splits);
+        GPX_DISPATCH_FAMILY(h->kp.family, rc = (launch_ivar_ws<FAM>(a, h->kp, grid, st)));
+        return rc;
+    }
+    GPX_DISPATCH_FAMILY(h->kp.family, rc = (launch_core<FAM, EPI_IVAR, true>(a, h->kp, (C + BN - 1) / BN, splits, st)));
     return rc;
 }
 
@@ -405,8 +813,8 @@ int gpx_launch_core_store(gpx_handle h, const double* A, int64_t lda, const doub
     a.dpad = (h->kp.d + 3) & ~3;
     a.tiles_per_cta = 1;
     a.upper_only = 0;
-    dim3 grid((unsigned)((J + BN - 1) / BN), (unsigned)((I + BM - 1) / BM));
-    GPX_DISPATCH_FAMILY(h->kp.family, rc = (launch_core<FAM, EPI_STORE, true>(a, h->kp, grid, st)));
+    GPX_DISPATCH_FAMILY(h->kp.family,
+                        rc = (launch_core<FAM, EPI_STORE, true>(a, h->kp, (J + BN - 1) / BN, (I + core_bm() - 1) / core_bm(), st)));
     return rc;
 }
 
@@ -416,7 +824,7 @@ extern "C" int gpx_dgemm_tn_sub(gpx_handle h, const double* A, int64_t lda, cons
     GPX_REQUIRE(I >= 0 && J >= 0 && K >= 0, GPX_EINVAL, "negative size");
     if (I == 0 || J == 0 || K == 0) return GPX_OK;
     GPX_REQUIRE(A && B && C, GPX_EINVAL, "NULL pointer");
-    GPX_REQUIRE((I + BM - 1) / BM <= 65535, GPX_ESIZE, "I too large for one launch");
+    GPX_REQUIRE((I + 63) / 64 <= 65535, GPX_ESIZE, "I too large for one launch");
     int rc;
     if ((rc = check_operand(A, lda, "A"))) return rc;
     if ((rc = check_operand(B, ldb, "B"))) return rc;
@@ -436,8 +844,7 @@ extern "C" int gpx_dgemm_tn_sub(gpx_handle h, const double* A, int64_t lda, cons
     a.tiles_per_cta = 1;
     a.upper_only = upper_only;
     KParams kp = h->kp;
-    dim3 grid((unsigned)((J + BN - 1) / BN), (unsigned)((I + BM - 1) / BM));
-    return launch_core<GPX_SE, EPI_SUB, false>(a, kp, grid, (cudaStream_t)stream);
+    return launch_core<GPX_SE, EPI_SUB, false>(a, kp, (J + BN - 1) / BN, (I + core_bm() - 1) / core_bm(), (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------
