@@ -27,6 +27,40 @@
 
 namespace {
 
+// 2^(j/256): table-driven exp for the covariance prologue of the hot kernel.  exp(x) = 2^k * T[j] * e^r with
+// n = rint(x * 256/ln2) = 256 k + j and |r| <= ln2/512, e^r - 1 by a degree-4 polynomial: 9 FP64-pipe
+// operations and one shared-memory lookup per value, <= 1 ulp (libdevice exp: 19 FP64 + 26 other instructions).
+__device__ const double gpx_exp2_tab[256] = {
+#include "gpx_exp_table.inc"
+};
+
+__device__ __forceinline__ double gpx_exp_tab(double x, const double* __restrict__ tab) {
+    const double MAGIC = 6755399441055744.0;                    // 1.5 * 2^52
+    const double t = fma(x, 0x1.71547652b82fep+8, MAGIC);       // x * 256/ln2, rounded to an integer in the low word
+    const int n = __double2loint(t);
+    const double nf = t - MAGIC;
+    double r = fma(nf, -0x1.62e42fef80000p-9, x);               // ln2/256 split hi (exact products) + lo
+    r = fma(nf, -0x1.1cf79abc9e3b4p-44, r);
+    double p = fma(1.0 / 24.0, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    const double q = p * r;                                     // e^r - 1
+    const double tj = tab[n & 255];
+    double res = fma(tj, q, tj);
+    res = __hiloint2double(__double2hiint(res) + ((n >> 8) << 20), __double2loint(res));  // * 2^k
+    return n < -261632 ? 0.0 : res;                             // below 2^-1022: flush (x < -708.4)
+}
+
+// expanded-form covariance with the table exp; tab already carries the signal variance
+template <int FAM>
+__device__ __forceinline__ double kexpand_tab(double e, const KParams& kp, const double* __restrict__ tab) {
+    if (FAM == GPX_MATERN32) {
+        const double t = kp.c0 * sqrt(fmax(e, 0.0));
+        return (1.0 + t) * gpx_exp_tab(-t, tab);
+    }
+    return gpx_exp_tab(e, tab);
+}
+
 constexpr int BN = 128;
 constexpr int BK = 16;
 constexpr int STAGES = 4;
@@ -390,7 +424,7 @@ constexpr int WS_LD = 132;
 constexpr int WS_STAGE = BK * 2 * WS_LD;  // doubles
 constexpr int WS_STAGES = 6;               // ring depth
 constexpr int WS_AHEAD = 3;                // chunks in flight; the refilled stage was released 3 chunks ago
-constexpr int WS_SMEM_DOUBLES = WS_STAGES * WS_STAGE + WS_STAGES * WS_BM + BN + 4 * BN + 2 * WS_STAGES;
+constexpr int WS_SMEM_DOUBLES = WS_STAGES * WS_STAGE + WS_STAGES * WS_BM + BN + 4 * BN + 2 * WS_STAGES + 256;
 constexpr size_t WS_SMEM_BYTES = (size_t)WS_SMEM_DOUBLES * sizeof(double);
 
 __device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
@@ -432,6 +466,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
     double* s_red = s_beta + BN;
     uint64_t* full = reinterpret_cast<uint64_t*>(s_red + 4 * BN);
     uint64_t* empty = full + WS_STAGES;
+    double* s_tab = reinterpret_cast<double*>(empty + WS_STAGES);  // signal * 2^(j/256)
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -454,6 +489,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (tid < BN) s_beta[tid] = (j0 + tid < a.J) ? a.Bs[j0 + tid] : 0.0;
+    s_tab[tid] = kp.signal * gpx_exp2_tab[tid];
     __syncthreads();
 
     double rs[2] = {0.0, 0.0};
@@ -566,7 +602,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const double be = s_beta[wn * 64 + (u >> 1) * 16 + (q4 * 2 + e) * 2 + (u & 1)];
-                            acc[t][u][e] = -kexpand<FAM>(acc[t][u][e] + al + be, kp);
+                            acc[t][u][e] = -kexpand_tab<FAM>(acc[t][u][e] + al + be, kp, s_tab);
                         }
                 }
             }
