@@ -48,35 +48,35 @@ extern "C" int gpx_prior_diag(gpx_handle h, const double* X, int64_t n, int64_t 
 // ---------------------------------------------------------------------------------------------
 #define GRAM_ROWS 16
 
-template <int FAM>
+template <int FAM, int D>
 __global__ void __launch_bounds__(256) gram_kernel(const __grid_constant__ KParams kp, const double* __restrict__ X,
                                                     int64_t nx, int64_t ldx, const double* __restrict__ Y, int64_t ny,
                                                     int64_t ldy, double* __restrict__ out, int64_t ld, int add_diag,
                                                     const double* __restrict__ nugvec, double nug) {
-    __shared__ double sx[GPX_MAX_DIM][GRAM_ROWS];
-    const int d = kp.d;
+    __shared__ double sx[D][GRAM_ROWS];
+    __shared__ double s_tab[256];
+    s_tab[threadIdx.x] = kp.signal * gpx_exp2_tab[threadIdx.x];
     const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    double y[GPX_MAX_DIM];
+    double y[D];
 #pragma unroll
-    for (int i = 0; i < GPX_MAX_DIM; ++i) y[i] = (i < d && j < ny) ? Y[i * ldy + j] : 0.0;
+    for (int i = 0; i < D; ++i) y[i] = (j < ny) ? Y[i * ldy + j] : 0.0;
 
     for (int64_t i0 = (int64_t)blockIdx.y * GRAM_ROWS; i0 < nx; i0 += (int64_t)gridDim.y * GRAM_ROWS) {
         __syncthreads();
-        if (threadIdx.x < GRAM_ROWS * d) {
+        if (threadIdx.x < GRAM_ROWS * D) {
             const int i = threadIdx.x / GRAM_ROWS, r = threadIdx.x % GRAM_ROWS;
             sx[i][r] = (i0 + r < nx) ? X[i * ldx + i0 + r] : 0.0;
         }
         __syncthreads();
         if (j < ny) {
+            const int rows = (nx - i0) < GRAM_ROWS ? (int)(nx - i0) : GRAM_ROWS;
 #pragma unroll 4
-            for (int r = 0; r < GRAM_ROWS; ++r) {
+            for (int r = 0; r < rows; ++r) {
                 const int64_t row = i0 + r;
-                if (row >= nx) break;
                 double acc = 0.0;
 #pragma unroll
-                for (int i = 0; i < GPX_MAX_DIM; ++i)
-                    if (i < d) kacc_dim<FAM>(acc, kp, i, sx[i][r], y[i]);
-                double v = kfinish<FAM>(acc, kp);
+                for (int i = 0; i < D; ++i) kacc_dim<FAM>(acc, kp, i, sx[i][r], y[i]);
+                double v = kfinish_tab<FAM>(acc, kp, s_tab);
                 if (add_diag && row == j) v += nugvec ? nugvec[row] : nug;
                 __stcs(out + row * ld + j, v);
             }
@@ -94,8 +94,8 @@ extern "C" int gpx_gram(gpx_handle h, const double* X, int64_t nx, int64_t ldx, 
     int64_t gy = (nx + GRAM_ROWS - 1) / GRAM_ROWS;
     if (gy > 32768) gy = 32768;
     dim3 grid((unsigned)((ny + 255) / 256), (unsigned)gy);
-    GPX_DISPATCH_FAMILY(h->kp.family, (gram_kernel<FAM><<<grid, 256, 0, st>>>(h->kp, X, nx, ldx, Y, ny, ldy, out, ld,
-                                                                           add_diag, nugget_vec, nugget)));
+    GPX_DISPATCH_FAMILY(h->kp.family, GPX_DISPATCH_DIM(h->kp.d, (gram_kernel<FAM, D><<<grid, 256, 0, st>>>(
+                                                                    h->kp, X, nx, ldx, Y, ny, ldy, out, ld, add_diag, nugget_vec, nugget))));
     return gpx_check_launch("gpx_gram");
 }
 
@@ -304,12 +304,22 @@ __global__ void __launch_bounds__(128) append_row_kernel(const __grid_constant__
     const double* wp = W + j;
     double a0 = 0.0, a1 = 0.0;
     int i = 0;
-    for (; i + 8 <= n; i += 8) {
-        double2 w[8];
+    for (; i + 16 <= n; i += 16) {
+        double2 w[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) w[u] = __ldcs(reinterpret_cast<const double2*>(wp + (int64_t)(i + u) * ldw));
+        for (int u = 0; u < 16; ++u) w[u] = __ldcs(reinterpret_cast<const double2*>(wp + (int64_t)(i + u) * ldw));
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 16; ++u) {
+            a0 = fma(sl[i + u], w[u].x, a0);
+            a1 = fma(sl[i + u], w[u].y, a1);
+        }
+    }
+    for (; i + 4 <= n; i += 4) {
+        double2 w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) w[u] = __ldcs(reinterpret_cast<const double2*>(wp + (int64_t)(i + u) * ldw));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
             a0 = fma(sl[i + u], w[u].x, a0);
             a1 = fma(sl[i + u], w[u].y, a1);
         }

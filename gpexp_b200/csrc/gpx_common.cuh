@@ -86,6 +86,41 @@ __device__ __forceinline__ double kfinish(double acc, const KParams& kp) {
     return kp.signal * exp(-acc);
 }
 
+// 2^(j/256): table-driven exp used by the covariance prologue of the hot kernel and by the Gram kernel.  exp(x) = 2^k * T[j] * e^r with
+// n = rint(x * 256/ln2) = 256 k + j and |r| <= ln2/512, e^r - 1 by a degree-4 polynomial: 9 FP64-pipe
+// operations and one shared-memory lookup per value, <= 1 ulp (libdevice exp: 19 FP64 + 26 other instructions).
+static __device__ const double gpx_exp2_tab[256] = {
+#include "gpx_exp_table.inc"
+};
+
+__device__ __forceinline__ double gpx_exp_tab(double x, const double* __restrict__ tab) {
+    const double MAGIC = 6755399441055744.0;                    // 1.5 * 2^52
+    const double t = fma(x, 0x1.71547652b82fep+8, MAGIC);       // x * 256/ln2, rounded to an integer in the low word
+    const int n = __double2loint(t);
+    const double nf = t - MAGIC;
+    double r = fma(nf, -0x1.62e42fef80000p-9, x);               // ln2/256 split hi (exact products) + lo
+    r = fma(nf, -0x1.1cf79abc9e3b4p-44, r);
+    double p = fma(1.0 / 24.0, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    const double q = p * r;                                     // e^r - 1
+    const double tj = tab[n & 255];
+    double res = fma(tj, q, tj);
+    res = __hiloint2double(__double2hiint(res) + ((n >> 8) << 20), __double2loint(res));  // * 2^k
+    return n < -261632 ? 0.0 : res;                             // below 2^-1022: flush (x < -708.4)
+}
+
+// difference-form finish with the table exp; `tab` already carries the signal variance (tab[j] = signal * 2^(j/256))
+template <int FAM>
+__device__ __forceinline__ double kfinish_tab(double acc, const KParams& kp, const double* __restrict__ tab) {
+    if (FAM == GPX_SE) return gpx_exp_tab(-0.5 * acc, tab);
+    if (FAM == GPX_MATERN32) {
+        const double t = kp.c0 * sqrt(acc);
+        return (1.0 + t) * gpx_exp_tab(-t, tab);
+    }
+    return gpx_exp_tab(-acc, tab);
+}
+
 // Expanded form used by the tensor-core prologue:  k = kexpand(alpha(x) + beta(y) + sum_i u_i(x) v_i(y)).
 template <int FAM>
 __device__ __forceinline__ double kexpand(double e, const KParams& kp) {
@@ -95,6 +130,22 @@ __device__ __forceinline__ double kexpand(double e, const KParams& kp) {
     }
     return kp.signal * exp(e);
 }
+
+#define GPX_DIM_CASE(n, ...)     \
+    case n: {                    \
+        constexpr int D = n;     \
+        __VA_ARGS__;             \
+    } break;
+#define GPX_DISPATCH_DIM(d, ...)                                                                            \
+    switch (d) {                                                                                            \
+        GPX_DIM_CASE(1, __VA_ARGS__) GPX_DIM_CASE(2, __VA_ARGS__) GPX_DIM_CASE(3, __VA_ARGS__)             \
+        GPX_DIM_CASE(4, __VA_ARGS__) GPX_DIM_CASE(5, __VA_ARGS__) GPX_DIM_CASE(6, __VA_ARGS__)             \
+        GPX_DIM_CASE(7, __VA_ARGS__) GPX_DIM_CASE(8, __VA_ARGS__) GPX_DIM_CASE(9, __VA_ARGS__)             \
+        GPX_DIM_CASE(10, __VA_ARGS__) GPX_DIM_CASE(11, __VA_ARGS__) GPX_DIM_CASE(12, __VA_ARGS__)          \
+        GPX_DIM_CASE(13, __VA_ARGS__) GPX_DIM_CASE(14, __VA_ARGS__) GPX_DIM_CASE(15, __VA_ARGS__)          \
+        GPX_DIM_CASE(16, __VA_ARGS__)                                                                       \
+        default: break;                                                                                     \
+    }
 
 #define GPX_DISPATCH_FAMILY(fam, ...)                         \
     do {                                                      \

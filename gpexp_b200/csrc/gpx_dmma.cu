@@ -27,30 +27,6 @@
 
 namespace {
 
-// 2^(j/256): table-driven exp for the covariance prologue of the hot kernel.  exp(x) = 2^k * T[j] * e^r with
-// n = rint(x * 256/ln2) = 256 k + j and |r| <= ln2/512, e^r - 1 by a degree-4 polynomial: 9 FP64-pipe
-// operations and one shared-memory lookup per value, <= 1 ulp (libdevice exp: 19 FP64 + 26 other instructions).
-__device__ const double gpx_exp2_tab[256] = {
-#include "gpx_exp_table.inc"
-};
-
-__device__ __forceinline__ double gpx_exp_tab(double x, const double* __restrict__ tab) {
-    const double MAGIC = 6755399441055744.0;                    // 1.5 * 2^52
-    const double t = fma(x, 0x1.71547652b82fep+8, MAGIC);       // x * 256/ln2, rounded to an integer in the low word
-    const int n = __double2loint(t);
-    const double nf = t - MAGIC;
-    double r = fma(nf, -0x1.62e42fef80000p-9, x);               // ln2/256 split hi (exact products) + lo
-    r = fma(nf, -0x1.1cf79abc9e3b4p-44, r);
-    double p = fma(1.0 / 24.0, r, 1.0 / 6.0);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    const double q = p * r;                                     // e^r - 1
-    const double tj = tab[n & 255];
-    double res = fma(tj, q, tj);
-    res = __hiloint2double(__double2hiint(res) + ((n >> 8) << 20), __double2loint(res));  // * 2^k
-    return n < -261632 ? 0.0 : res;                             // below 2^-1022: flush (x < -708.4)
-}
-
 // expanded-form covariance with the table exp; tab already carries the signal variance
 template <int FAM>
 __device__ __forceinline__ double kexpand_tab(double e, const KParams& kp, const double* __restrict__ tab) {
