@@ -62,7 +62,8 @@ SIGNATURES = {
     "gpx_score_ivar": [_p, _p, _i64, _p, _p, _p, _i64, _p, _i64, _p, _p, _p, _i64, _i64, _dbl, _dbl, _p, _p, _p, _p,
                        _p, _p],
     "gpx_score_mi": [_p, _p, _p, _dbl, _p, _i64, _p, _p, _p, _p],
-    "gpx_mi_prec_column": [_p, _p, _i64, _i64, _p, _p, _p],
+    "gpx_mi_prec_column_workspace": [_i64, _i64],
+    "gpx_mi_prec_column": [_p, _p, _i64, _i64, _p, _p, _p, _p],
     "gpx_colsumsq": [_p, _p, _i64, _i64, _i64, _p, _p, _p],
     "gpx_transpose": [_p, _p, _i64, _i64, _i64, _p, _i64, _p],
     "gpx_set_mask": [_p, _p, _p, C.c_uint8, _p],
@@ -70,7 +71,7 @@ SIGNATURES = {
     "gpx_bench_dmma": [_p, _i64, _p, _p],
     "gpx_bench_dfma": [_p, _i64, _p, _p],
 }
-_RESTYPES = {"gpx_last_error": C.c_char_p, "gpx_score_ivar_workspace": _i64}
+_RESTYPES = {"gpx_last_error": C.c_char_p, "gpx_score_ivar_workspace": _i64, "gpx_mi_prec_column_workspace": _i64}
 
 for _name, _args in SIGNATURES.items():
     _fn = getattr(lib, _name)  # AttributeError here == the .so does not export a declared symbol

@@ -599,44 +599,82 @@ extern "C" int gpx_score_mi(gpx_handle h, const double* num_var, const double* p
     return gpx_argreduce_impl(h, score_out, nullptr, mask, n, 0, best, idx, st);
 }
 
-// out[i] = sum_{k >= max(i,p)} Y[k,i] * Y[k,p]   (Y lower triangular, row-major)
-__global__ void __launch_bounds__(128) mi_prec_column_kernel(const double* __restrict__ Y, int64_t n, int64_t ldy,
-                                                              const int64_t* __restrict__ pdev, double* __restrict__ out) {
+// out[i] = sum_{k >= max(i,p)} Y[k,i] * Y[k,p]   (Y lower triangular, row-major).  Reads ~4 n^2 bytes.
+// 2-D decomposition: a block owns 256 columns x MI_KCH rows and writes one partial per column; the partials
+// are added in row-chunk order by a second kernel (deterministic).  Blocks above the diagonal write zeros.
+#define MI_KCH 256
+
+__global__ void __launch_bounds__(128) mi_prec_partial_kernel(const double* __restrict__ Y, int64_t n, int64_t ldy,
+                                                               const int64_t* __restrict__ pdev, double* __restrict__ part) {
+    __shared__ double syp[MI_KCH];
     const int64_t p = pdev[0];
     const int64_t i = ((int64_t)blockIdx.x * 128 + threadIdx.x) * 2;
-    if (i >= n || p < 0) return;
-    // both columns i, i+1 start at k = max(i,p) (Y[i, i+1] = 0 is stored explicitly)
-    int64_t k = i > p ? i : p;
-    double a0 = 0.0, a1 = 0.0;
-    for (; k + 4 <= n; k += 4) {
-        double2 y[4];
-        double yp[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            y[u] = *reinterpret_cast<const double2*>(Y + (k + u) * ldy + i);
-            yp[u] = __ldg(Y + (k + u) * ldy + p);
+    const int64_t k0 = (int64_t)blockIdx.y * MI_KCH;
+    int64_t k1 = k0 + MI_KCH;
+    if (k1 > n) k1 = n;
+    double* dst = part + (int64_t)blockIdx.y * ldy;
+    const int64_t i0 = (int64_t)blockIdx.x * 256;
+    const int64_t lo_blk = i0 > p ? i0 : p;
+    if (p < 0 || k1 <= lo_blk) {  // nothing in this row chunk reaches these columns
+        if (i < n) {
+            dst[i] = 0.0;
+            if (i + 1 < n) dst[i + 1] = 0.0;
         }
+        return;
+    }
+    for (int t = threadIdx.x; t < MI_KCH; t += 128) syp[t] = (k0 + t < k1) ? Y[(k0 + t) * ldy + p] : 0.0;
+    __syncthreads();
+    if (i >= n) return;
+    int64_t k = i > p ? i : p;  // column i+1 also starts here: Y[i, i+1] = 0 is stored explicitly
+    if (k < k0) k = k0;
+    double a0 = 0.0, a1 = 0.0;
+    for (; k + 4 <= k1; k += 4) {
+        double2 y[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) y[u] = __ldcs(reinterpret_cast<const double2*>(Y + (k + u) * ldy + i));
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            a0 = fma(y[u].x, yp[u], a0);
-            a1 = fma(y[u].y, yp[u], a1);
+            const double yp = syp[k + u - k0];
+            a0 = fma(y[u].x, yp, a0);
+            a1 = fma(y[u].y, yp, a1);
         }
     }
-    for (; k < n; ++k) {
-        const double2 y = *reinterpret_cast<const double2*>(Y + k * ldy + i);
-        const double yp = __ldg(Y + k * ldy + p);
+    for (; k < k1; ++k) {
+        const double2 y = __ldcs(reinterpret_cast<const double2*>(Y + k * ldy + i));
+        const double yp = syp[k - k0];
         a0 = fma(y.x, yp, a0);
         a1 = fma(y.y, yp, a1);
     }
-    out[i] = a0;
-    if (i + 1 < n) out[i + 1] = a1;
+    dst[i] = a0;
+    if (i + 1 < n) dst[i + 1] = a1;
 }
 
-extern "C" int gpx_mi_prec_column(gpx_handle h, const double* Y, int64_t n, int64_t ldy, const int64_t* p_dev, double* out,
-                                  void* stream) {
-    GPX_REQUIRE(h && Y && p_dev && out && n >= 1, GPX_EINVAL, "bad arguments");
+__global__ void __launch_bounds__(256) mi_prec_reduce_kernel(const double* __restrict__ part, int nchunks, int64_t n,
+                                                              int64_t ldy, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int c = 0; c < nchunks; ++c) s += part[(int64_t)c * ldy + i];
+    out[i] = s;
+}
+
+extern "C" int64_t gpx_mi_prec_column_workspace(int64_t n, int64_t ldy) {
+    if (n <= 0) return 0;
+    return ((n + MI_KCH - 1) / MI_KCH) * ldy;
+}
+
+extern "C" int gpx_mi_prec_column(gpx_handle h, const double* Y, int64_t n, int64_t ldy, const int64_t* p_dev,
+                                  double* workspace, double* out, void* stream) {
+    GPX_REQUIRE(h && Y && p_dev && out && workspace && n >= 1, GPX_EINVAL, "bad arguments");
     GPX_REQUIRE((ldy % 2) == 0 && ldy >= n + (n & 1) && gpx_aligned16(Y), GPX_EALIGN,
                 "Y must be 16-byte aligned with an even leading dimension");
-    mi_prec_column_kernel<<<(unsigned)((n + 255) / 256), 128, 0, (cudaStream_t)stream>>>(Y, n, ldy, p_dev, out);
-    return gpx_check_launch("gpx_mi_prec_column");
+    const int64_t nchunks = (n + MI_KCH - 1) / MI_KCH;
+    GPX_REQUIRE(nchunks <= 65535, GPX_ESIZE, "pool too large for one launch");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)nchunks);
+    mi_prec_partial_kernel<<<grid, 128, 0, st>>>(Y, n, ldy, p_dev, workspace);
+    int rc = gpx_check_launch("gpx_mi_prec_column partial");
+    if (rc) return rc;
+    mi_prec_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(workspace, (int)nchunks, n, ldy, out);
+    return gpx_check_launch("gpx_mi_prec_column reduce");
 }

@@ -21,6 +21,7 @@ constexpr int SLD = NB + 1;      // padded shared-memory stride
 // On exit col[i] (i <= j) = U[i][j].  Returns 0 or 1 + local index of the first non-positive pivot.
 __device__ __forceinline__ int warp_potf2_32(double (&col)[32], int lane) {
     int bad = 0;
+    // both loops are fully unrolled with compile-time (k, i) so that col[] stays in registers
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
         const double akk = __shfl_sync(0xffffffffu, col[k], k);
@@ -29,9 +30,11 @@ __device__ __forceinline__ int warp_potf2_32(double (&col)[32], int lane) {
         if (lane == k) col[k] = dkk;
         if (lane > k) col[k] = col[k] / dkk;  // U[k][lane]
 #pragma unroll
-        for (int i = k + 1; i < 32; ++i) {
-            const double uki = __shfl_sync(0xffffffffu, col[k], i);  // U[k][i]
-            if (lane >= i) col[i] = fma(-uki, col[k], col[i]);
+        for (int i = 0; i < 32; ++i) {
+            if (i > k) {
+                const double uki = __shfl_sync(0xffffffffu, col[k], i);  // U[k][i]
+                if (lane >= i) col[i] = fma(-uki, col[k], col[i]);
+            }
         }
     }
     return bad;

@@ -367,6 +367,7 @@ class GreedyMIEngine(_Pivoting):
         self.info = info
         self.Us = dev.zeros(ncap, ld)         # downdate vectors u_s
         self.pcol = dev.zeros(ld)
+        self.pws = dev.zeros(max(int(lib.gpx_mi_prec_column_workspace(v, ld)), 1))
         self.rec2 = dev.zeros(self.reclen)
         self.mask = dev.zeros(ld, dtype=torch.uint8)
         self.scores = dev.zeros(ld)
@@ -383,13 +384,14 @@ class GreedyMIEngine(_Pivoting):
         self._gather(self.W, ld, self.num, pool, self.noise, minimize=False)
         check(lib.gpx_append_row(dev.h, _lib.ROW_KERNEL, ptr(self.rec), None, ptr(pool.X), v, ld, ptr(self.W), ld, self.n,
                                  ptr(self.num), dev.stream), "gpx_append_row")
-        check(lib.gpx_mi_prec_column(dev.h, ptr(self.Y), v, ld, ptr(self.idx), ptr(self.pcol), dev.stream), "gpx_mi_prec_column")
+        check(lib.gpx_mi_prec_column(dev.h, ptr(self.Y), v, ld, ptr(self.idx), ptr(self.pws), ptr(self.pcol), dev.stream),
+              "gpx_mi_prec_column")
         check(lib.gpx_gather_pivot(dev.h, ptr(self.Us), ld, self.n, ptr(self.pd), ptr(pool.X), ld, None, ptr(self.idx), 0, 0.0,
                                    ptr(self.rec2), dev.stream), "gpx_gather_pivot")
         check(lib.gpx_append_row(dev.h, _lib.ROW_MATRIX, ptr(self.rec2), ptr(self.pcol), None, v, ld, ptr(self.Us), ld, self.n,
                                  ptr(self.pd), dev.stream), "gpx_append_row")
         check(lib.gpx_set_mask(dev.h, ptr(self.mask), ptr(self.idx), 1, dev.stream), "gpx_set_mask")
-        dev.launches += 6
+        dev.launches += 7
         self._record()
         self.n += 1
 

@@ -183,9 +183,11 @@ int gpx_score_ivar(gpx_handle h, const double* Wm, int64_t ldm, const double* va
 int gpx_score_mi(gpx_handle h, const double* num_var, const double* prec_diag, double noise, const uint8_t* mask,
                  int64_t n, double* score_out, double* best, int64_t* idx, void* stream);
 
-/* K6  column p of P = Y^T Y for the lower-triangular Y = U^-T (row-major):  out[i] = sum_k Y[k,i] Y[k,p]. */
-int gpx_mi_prec_column(gpx_handle h, const double* Y, int64_t n, int64_t ldy, const int64_t* p_dev, double* out,
-                       void* stream);
+/* K6  column p of P = Y^T Y for the lower-triangular Y = U^-T (row-major):  out[i] = sum_k Y[k,i] Y[k,p].
+ *     workspace: gpx_mi_prec_column_workspace(n, ldy) doubles (row-chunk partials, added in a fixed order). */
+int64_t gpx_mi_prec_column_workspace(int64_t n, int64_t ldy);
+int gpx_mi_prec_column(gpx_handle h, const double* Y, int64_t n, int64_t ldy, const int64_t* p_dev, double* workspace,
+                       double* out, void* stream);
 
 /* Column sums of squares: out[j] = sum_{i<n} W[i,j]^2 (optionally out[j] = base[j] - that). */
 int gpx_colsumsq(gpx_handle h, const double* W, int64_t n, int64_t ncols, int64_t ldw, const double* base,

@@ -262,7 +262,8 @@ def test_potrf_trsm_blocks(gx, n):
     # a column of the precision from Y
     p = dev.upload(np.array([n // 2], dtype=np.int64), dtype=gx.torch.int64)
     col = dev.zeros(ld)
-    gx.check(lib.gpx_mi_prec_column(dev.h, ptr(Y), n, ld, ptr(p), ptr(col), dev.stream))
+    ws = dev.zeros(max(int(lib.gpx_mi_prec_column_workspace(n, ld)), 1))
+    gx.check(lib.gpx_mi_prec_column(dev.h, ptr(Y), n, ld, ptr(p), ptr(ws), ptr(col), dev.stream))
     np.testing.assert_allclose(col[:n].cpu().numpy(), np.linalg.inv(A)[:, n // 2], rtol=1e-7, atol=1e-9)
     # rank-1 append reproduces the factor of the bordered matrix
     if n >= 2:
@@ -430,3 +431,59 @@ def test_posterior_variance_large_vs_oracle(gx):
     var = g.evaluateVariance(query)
     ref = orc.fast_posterior_variance(ks, nodes, query, 1e-6)
     assert np.max(np.abs(var - ref)) <= 1e-9 * np.max(ks.prior(query))
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configurations at (or near) full size: properties + oracle spot checks
+# ------------------------------------------------------------------------------------------------
+def test_cfg3_full_size_conditional_entropy(gx):
+    """cfg-3 in full: 5-D Matern, 1 024 points from 250 000 candidates.  Oracle indices for the first 60 steps,
+    size-independent properties for the rest."""
+    rng = np.random.default_rng(3)
+    C, N = 250_000, 1024
+    pool = rng.uniform(-1, 1, (C, 5))
+    ks = spec("matern_5d")
+    bind(gx, "matern_5d")
+    eng = gx.engine.GreedyVarEngine(gx.dev, gx.dev.points(pool), N)
+    idx = eng.run(N)
+    ref, _ = orc.fast_greedy_var(ks, pool, 60)
+    assert [int(i) for i in idx[:60]] == ref
+    assert len(set(int(i) for i in idx)) == N
+    sel = gx.torch.as_tensor(idx, device=eng.W.device)
+    L = eng.W[:N][:, sel].cpu().numpy().T
+    np.testing.assert_allclose(L @ L.T, ks.gram(pool[idx], pool[idx]), rtol=0, atol=1e-11)
+    assert np.all(np.diff(eng.pick_scores[:N].cpu().numpy()) <= 1e-12)
+    # selected points have (numerically) zero remaining variance, everything else is positive
+    var = eng.var[:C].cpu().numpy()
+    assert np.max(np.abs(var[idx])) <= 1e-12 and var.min() >= -1e-12
+
+
+def test_cfg2_mid_size_greedy_ivar_vs_oracle(gx):
+    rng = np.random.default_rng(2)
+    C, M, N = 5000, 12000, 16
+    cand, mc = rng.uniform(-1, 1, (C, 2)), rng.uniform(-1, 1, (M, 2))
+    ks, k = spec("se_ard_2d"), product_kernel("se_ard_2d")
+    ref, costs = orc.fast_greedy_ivar(ks, cand, mc, N, 1e-6)
+    cf = gx.ed.costFunctionGP_IVAR(gx.gp.GP(k, 1e-6), 1, gx.Space(2, None, None), mcPoints=mc)
+    idx = gx.ed.performGreedyIVARExperimentalDesign(cf, cand, N, returnIndices=True)
+    assert [int(i) for i in idx] == ref
+    want = np.array([c[i] for c, i in zip(costs, ref)])
+    assert np.max(np.abs(cf.lastScores - want) / np.abs(want)) <= 1e-9
+
+
+def test_cfg5_shape_step_vs_oracle_subset(gx):
+    """cfg-5 operand shape (10-D ARD, long K loop, several M-splits) at n = 1024: one scoring step from a given
+    design; every 300th candidate and the arg-min are checked against the oracle."""
+    rng = np.random.default_rng(5)
+    C, M, n, d = 20_000, 30_000, 1024, 10
+    cand, mc = rng.uniform(-1, 1, (C, d)), rng.uniform(-1, 1, (M, d))
+    design = cand[rng.permutation(C)[:n]]
+    ks, k = spec("se_ard_10d"), product_kernel("se_ard_10d")
+    cf = gx.ed.costFunctionGP_IVAR(gx.gp.GP(k, 1e-6), 1, gx.Space(d, None, None), mcPoints=mc)
+    costs, best = gx.ed.scoreCandidatesIVAR(cf, design, cand)
+    sub = np.unique(np.concatenate([[best], np.arange(0, C, 300)]))
+    w_m, var_m = orc.fast_design_state(ks, design, mc, 1e-6)
+    w_c, var_c = orc.fast_design_state(ks, design, cand[sub], 1e-6)
+    ref = orc.fast_ivar_scores(ks, cand[sub], mc, w_m, var_m, w_c, var_c, 1e-6)
+    assert np.max(np.abs(costs[sub] - ref) / np.abs(ref)) <= 1e-9
+    assert costs[best] == costs.min()
