@@ -52,15 +52,18 @@ template <int FAM, int D>
 __global__ void __launch_bounds__(256) gram_kernel(const __grid_constant__ KParams kp, const double* __restrict__ X,
                                                     int64_t nx, int64_t ldx, const double* __restrict__ Y, int64_t ny,
                                                     int64_t ldy, double* __restrict__ out, int64_t ld, int add_diag,
-                                                    const double* __restrict__ nugvec, double nug) {
+                                                    const double* __restrict__ nugvec, double nug, int vec2) {
     __shared__ double sx[D][GRAM_ROWS];
     __shared__ double s_tab[256];
     s_tab[threadIdx.x] = kp.signal * gpx_exp2_tab[threadIdx.x];
-    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    double y[D];
+    // two adjacent columns per thread (16-byte streaming stores) when the output rows are 16-byte aligned
+    const int64_t j = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 2;
+    double y0[D], y1[D];
 #pragma unroll
-    for (int i = 0; i < D; ++i) y[i] = (j < ny) ? Y[i * ldy + j] : 0.0;
-
+    for (int i = 0; i < D; ++i) {
+        y0[i] = (j < ny) ? Y[i * ldy + j] : 0.0;
+        y1[i] = (j + 1 < ny) ? Y[i * ldy + j + 1] : 0.0;
+    }
     for (int64_t i0 = (int64_t)blockIdx.y * GRAM_ROWS; i0 < nx; i0 += (int64_t)gridDim.y * GRAM_ROWS) {
         __syncthreads();
         if (threadIdx.x < GRAM_ROWS * D) {
@@ -73,12 +76,25 @@ __global__ void __launch_bounds__(256) gram_kernel(const __grid_constant__ KPara
 #pragma unroll 4
             for (int r = 0; r < rows; ++r) {
                 const int64_t row = i0 + r;
-                double acc = 0.0;
+                double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-                for (int i = 0; i < D; ++i) kacc_dim<FAM>(acc, kp, i, sx[i][r], y[i]);
-                double v = kfinish_tab<FAM>(acc, kp, s_tab);
-                if (add_diag && row == j) v += nugvec ? nugvec[row] : nug;
-                __stcs(out + row * ld + j, v);
+                for (int i = 0; i < D; ++i) {
+                    kacc_dim<FAM>(a0, kp, i, sx[i][r], y0[i]);
+                    kacc_dim<FAM>(a1, kp, i, sx[i][r], y1[i]);
+                }
+                double v0 = kfinish_tab<FAM>(a0, kp, s_tab);
+                double v1 = kfinish_tab<FAM>(a1, kp, s_tab);
+                if (add_diag) {
+                    if (row == j) v0 += nugvec ? nugvec[row] : nug;
+                    if (row == j + 1) v1 += nugvec ? nugvec[row] : nug;
+                }
+                double* dst = out + row * ld + j;
+                if (vec2 && j + 1 < ny) {
+                    __stcs(reinterpret_cast<double2*>(dst), make_double2(v0, v1));
+                } else {
+                    __stcs(dst, v0);
+                    if (j + 1 < ny) __stcs(dst + 1, v1);
+                }
             }
         }
     }
@@ -93,9 +109,10 @@ extern "C" int gpx_gram(gpx_handle h, const double* X, int64_t nx, int64_t ldx, 
     cudaStream_t st = (cudaStream_t)stream;
     int64_t gy = (nx + GRAM_ROWS - 1) / GRAM_ROWS;
     if (gy > 32768) gy = 32768;
-    dim3 grid((unsigned)((ny + 255) / 256), (unsigned)gy);
+    dim3 grid((unsigned)((ny + 511) / 512), (unsigned)gy);
+    const int vec2 = ((ld & 1) == 0 && gpx_aligned16(out)) ? 1 : 0;
     GPX_DISPATCH_FAMILY(h->kp.family, GPX_DISPATCH_DIM(h->kp.d, (gram_kernel<FAM, D><<<grid, 256, 0, st>>>(
-                                                                    h->kp, X, nx, ldx, Y, ny, ldy, out, ld, add_diag, nugget_vec, nugget))));
+                                                                    h->kp, X, nx, ldx, Y, ny, ldy, out, ld, add_diag, nugget_vec, nugget, vec2))));
     return gpx_check_launch("gpx_gram");
 }
 
