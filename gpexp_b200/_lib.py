@@ -63,7 +63,9 @@ SIGNATURES = {
                        _p, _p],
     "gpx_score_mi": [_p, _p, _p, _dbl, _p, _i64, _p, _p, _p, _p],
     "gpx_mi_prec_column_workspace": [_i64, _i64],
-    "gpx_mi_prec_column": [_p, _p, _i64, _i64, _p, _p, _p, _p],
+    "gpx_mi_prec_column": [_p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p],
+    "gpx_gather_column": [_p, _p, _i64, _i64, _p, _p, _p, _p],
+    "gpx_local_index": [_p, _p, _i64, _i64, _p, _p],
     "gpx_colsumsq": [_p, _p, _i64, _i64, _i64, _p, _p, _p],
     "gpx_transpose": [_p, _p, _i64, _i64, _i64, _p, _i64, _p],
     "gpx_set_mask": [_p, _p, _p, C.c_uint8, _p],

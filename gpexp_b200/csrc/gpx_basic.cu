@@ -621,28 +621,32 @@ extern "C" int gpx_score_mi(gpx_handle h, const double* num_var, const double* p
 // are added in row-chunk order by a second kernel (deterministic).  Blocks above the diagonal write zeros.
 #define MI_KCH 256
 
-__global__ void __launch_bounds__(128) mi_prec_partial_kernel(const double* __restrict__ Y, int64_t n, int64_t ldy,
-                                                               const int64_t* __restrict__ pdev, double* __restrict__ part) {
+__global__ void __launch_bounds__(128) mi_prec_partial_kernel(const double* __restrict__ Y, int64_t nrows, int64_t ncols,
+                                                               int64_t ldy, int64_t col_offset, const int64_t* __restrict__ pdev,
+                                                               const double* __restrict__ ycol, double* __restrict__ part) {
     __shared__ double syp[MI_KCH];
-    const int64_t p = pdev[0];
-    const int64_t i = ((int64_t)blockIdx.x * 128 + threadIdx.x) * 2;
+    const int64_t p = pdev[0];  // GLOBAL index of the pivot column
+    const int64_t i = ((int64_t)blockIdx.x * 128 + threadIdx.x) * 2;  // local column
     const int64_t k0 = (int64_t)blockIdx.y * MI_KCH;
     int64_t k1 = k0 + MI_KCH;
-    if (k1 > n) k1 = n;
+    if (k1 > nrows) k1 = nrows;
     double* dst = part + (int64_t)blockIdx.y * ldy;
-    const int64_t i0 = (int64_t)blockIdx.x * 256;
-    const int64_t lo_blk = i0 > p ? i0 : p;
+    const int64_t i0g = (int64_t)blockIdx.x * 256 + col_offset;  // smallest global column of the block
+    const int64_t lo_blk = i0g > p ? i0g : p;
     if (p < 0 || k1 <= lo_blk) {  // nothing in this row chunk reaches these columns
-        if (i < n) {
+        if (i < ncols) {
             dst[i] = 0.0;
-            if (i + 1 < n) dst[i + 1] = 0.0;
+            if (i + 1 < ncols) dst[i + 1] = 0.0;
         }
         return;
     }
-    for (int t = threadIdx.x; t < MI_KCH; t += 128) syp[t] = (k0 + t < k1) ? Y[(k0 + t) * ldy + p] : 0.0;
+    // column p of Y: from the dense vector when given (sharded pools), else from the local matrix
+    for (int t = threadIdx.x; t < MI_KCH; t += 128)
+        syp[t] = (k0 + t < k1) ? (ycol ? ycol[k0 + t] : Y[(k0 + t) * ldy + (p - col_offset)]) : 0.0;
     __syncthreads();
-    if (i >= n) return;
-    int64_t k = i > p ? i : p;  // column i+1 also starts here: Y[i, i+1] = 0 is stored explicitly
+    if (i >= ncols) return;
+    const int64_t ig = i + col_offset;
+    int64_t k = ig > p ? ig : p;  // column i+1 also starts here: Y[i, i+1] = 0 is stored explicitly
     if (k < k0) k = k0;
     double a0 = 0.0, a1 = 0.0;
     for (; k + 4 <= k1; k += 4) {
@@ -663,7 +667,7 @@ __global__ void __launch_bounds__(128) mi_prec_partial_kernel(const double* __re
         a1 = fma(y.y, yp, a1);
     }
     dst[i] = a0;
-    if (i + 1 < n) dst[i + 1] = a1;
+    if (i + 1 < ncols) dst[i + 1] = a1;
 }
 
 __global__ void __launch_bounds__(256) mi_prec_reduce_kernel(const double* __restrict__ part, int nchunks, int64_t n,
@@ -675,23 +679,61 @@ __global__ void __launch_bounds__(256) mi_prec_reduce_kernel(const double* __res
     out[i] = s;
 }
 
-extern "C" int64_t gpx_mi_prec_column_workspace(int64_t n, int64_t ldy) {
-    if (n <= 0) return 0;
-    return ((n + MI_KCH - 1) / MI_KCH) * ldy;
+extern "C" int64_t gpx_mi_prec_column_workspace(int64_t nrows, int64_t ldy) {
+    if (nrows <= 0) return 0;
+    return ((nrows + MI_KCH - 1) / MI_KCH) * ldy;
 }
 
-extern "C" int gpx_mi_prec_column(gpx_handle h, const double* Y, int64_t n, int64_t ldy, const int64_t* p_dev,
-                                  double* workspace, double* out, void* stream) {
-    GPX_REQUIRE(h && Y && p_dev && out && workspace && n >= 1, GPX_EINVAL, "bad arguments");
-    GPX_REQUIRE((ldy % 2) == 0 && ldy >= n + (n & 1) && gpx_aligned16(Y), GPX_EALIGN,
+extern "C" int gpx_mi_prec_column(gpx_handle h, const double* Y, int64_t nrows, int64_t ncols, int64_t ldy,
+                                  int64_t col_offset, const int64_t* p_dev, const double* ycol, double* workspace,
+                                  double* out, void* stream) {
+    GPX_REQUIRE(h && Y && p_dev && out && workspace && nrows >= 1 && ncols >= 1 && col_offset >= 0, GPX_EINVAL, "bad arguments");
+    GPX_REQUIRE((ldy % 2) == 0 && ldy >= ncols + (ncols & 1) && gpx_aligned16(Y), GPX_EALIGN,
                 "Y must be 16-byte aligned with an even leading dimension");
-    const int64_t nchunks = (n + MI_KCH - 1) / MI_KCH;
+    GPX_REQUIRE(ycol != nullptr || (col_offset == 0 && ncols == nrows), GPX_EINVAL,
+                "a column slice of Y needs the pivot column as a dense vector");
+    const int64_t nchunks = (nrows + MI_KCH - 1) / MI_KCH;
     GPX_REQUIRE(nchunks <= 65535, GPX_ESIZE, "pool too large for one launch");
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((unsigned)((n + 255) / 256), (unsigned)nchunks);
-    mi_prec_partial_kernel<<<grid, 128, 0, st>>>(Y, n, ldy, p_dev, workspace);
+    dim3 grid((unsigned)((ncols + 255) / 256), (unsigned)nchunks);
+    mi_prec_partial_kernel<<<grid, 128, 0, st>>>(Y, nrows, ncols, ldy, col_offset, p_dev, ycol, workspace);
     int rc = gpx_check_launch("gpx_mi_prec_column partial");
     if (rc) return rc;
-    mi_prec_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(workspace, (int)nchunks, n, ldy, out);
+    mi_prec_reduce_kernel<<<(unsigned)((ncols + 255) / 256), 256, 0, st>>>(workspace, (int)nchunks, ncols, ldy, out);
     return gpx_check_launch("gpx_mi_prec_column reduce");
+}
+
+// rec[2] = var[p] (if var), rec[HDR + i] = W[i, p] for i < n; no-op when *idx < 0 (the caller zeroes rec first:
+// the record is then summed across ranks, only the owner of p contributes)
+__global__ void __launch_bounds__(256) gather_column_kernel(const double* __restrict__ W, int64_t ldw, int64_t n,
+                                                             const double* __restrict__ var, const int64_t* __restrict__ idx,
+                                                             double* __restrict__ rec) {
+    const int64_t p = idx[0];
+    if (p < 0) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && var) rec[2] = var[p];
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
+        rec[GPX_PIVOT_HDR + i] = W[i * ldw + p];
+}
+
+extern "C" int gpx_gather_column(gpx_handle h, const double* W, int64_t ldw, int64_t n, const double* var,
+                                 const int64_t* idx_dev, double* rec, void* stream) {
+    GPX_REQUIRE(h && idx_dev && rec && n >= 0 && (W || n == 0), GPX_EINVAL, "bad arguments");
+    int64_t grid = (n + 255) / 256;
+    if (grid < 1) grid = 1;
+    if (grid > 1024) grid = 1024;
+    gather_column_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(W, ldw, n, var, idx_dev, rec);
+    return gpx_check_launch("gpx_gather_column");
+}
+
+// local index of a global pivot: out[0] = rec[1] - offset if it falls in [0, count), else -1
+__global__ void local_index_kernel(const double* __restrict__ rec, int64_t offset, int64_t count, int64_t* out) {
+    const int64_t g = (int64_t)rec[1] - offset;
+    out[0] = (rec[1] >= 0.0 && g >= 0 && g < count) ? g : -1;
+    out[1] = (int64_t)rec[1];
+}
+
+extern "C" int gpx_local_index(gpx_handle h, const double* rec, int64_t offset, int64_t count, int64_t* out2, void* stream) {
+    GPX_REQUIRE(h && rec && out2, GPX_EINVAL, "bad arguments");
+    local_index_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(rec, offset, count, out2);
+    return gpx_check_launch("gpx_local_index");
 }

@@ -384,8 +384,8 @@ class GreedyMIEngine(_Pivoting):
         self._gather(self.W, ld, self.num, pool, self.noise, minimize=False)
         check(lib.gpx_append_row(dev.h, _lib.ROW_KERNEL, ptr(self.rec), None, ptr(pool.X), v, ld, ptr(self.W), ld, self.n,
                                  ptr(self.num), dev.stream), "gpx_append_row")
-        check(lib.gpx_mi_prec_column(dev.h, ptr(self.Y), v, ld, ptr(self.idx), ptr(self.pws), ptr(self.pcol), dev.stream),
-              "gpx_mi_prec_column")
+        check(lib.gpx_mi_prec_column(dev.h, ptr(self.Y), v, v, ld, 0, ptr(self.idx), None, ptr(self.pws), ptr(self.pcol),
+                                     dev.stream), "gpx_mi_prec_column")
         check(lib.gpx_gather_pivot(dev.h, ptr(self.Us), ld, self.n, ptr(self.pd), ptr(pool.X), ld, None, ptr(self.idx), 0, 0.0,
                                    ptr(self.rec2), dev.stream), "gpx_gather_pivot")
         check(lib.gpx_append_row(dev.h, _lib.ROW_MATRIX, ptr(self.rec2), ptr(self.pcol), None, v, ld, ptr(self.Us), ld, self.n,
@@ -409,6 +409,161 @@ class GreedyMIEngine(_Pivoting):
         self.score()
         if self.score_trace is not None:
             self.score_trace.append(self.scores[: self.pool.n].cpu().numpy().copy())
+        self.take()
+
+    def run(self, n_points: int, start: int = 0):
+        if self.n == 0:
+            self.force(start)
+        while self.n < n_points:
+            self.step()
+        return self.indices()
+
+
+class ShardedMIEngine(_Pivoting):
+    """Greedy mutual information with the |V| x |V| matrices sharded by COLUMN BLOCKS over the ranks
+    (cfg-4 at full size: 200 000^2 doubles do not fit one GPU).
+
+    Set-up, left-looking in 128-row blocks, every rank holding its columns [lo, hi) of both matrices:
+        panel  P = U[0:kb, kb:kb+128]            broadcast from the owner of column block kb
+        U[kb blk, my cols >= kb]   = U_kk^-T (A[kb blk, .] - P^T U[0:kb, .])     DMMA update + forward substitution
+        Y[kb blk, my cols < kb+128] = U_kk^-T (I[kb blk, .] - P^T Y[0:kb, .])    (Y = U^-T, lower triangular)
+    so that K_VV + noise I = U^T U and (K_VV + noise I)^-1 = Y^T Y without any rank ever holding a full matrix.
+    Both updates reuse the same broadcast panel and together touch every local column once per block: balanced.
+    Per greedy step: one all_gather of numerator pivot records, one all_reduce that carries column p of Y (and of the
+    downdate vectors) from its owner to everybody, then purely local kernels.
+    """
+
+    BLK = 128
+
+    def __init__(self, dev: Device, pool_host: np.ndarray, n_max: int, noise: float, shard=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.noise = float(noise)
+        world = shard.world if shard is not None else 1
+        rank = shard.rank if shard is not None else 0
+        V = pool_host.shape[0]
+        self.V = V
+        nblk = (V + self.BLK - 1) // self.BLK
+        self.bounds = [min(Shard.split(nblk, world, r)[0] * self.BLK, V) for r in range(world)] + [V]
+        lo, hi = self.bounds[rank], self.bounds[rank + 1]
+        self.lo, self.hi = lo, hi
+        nloc = hi - lo
+        ncap = max(int(n_max), 1)
+        self._init_pivot(dev, ncap, n_max, shard, lo)
+        self.pool = dev.points(pool_host[lo:hi])
+        allpts = dev.points(pool_host)
+        ld = self.pool.ld
+        self.ld = ld
+        st = dev.stream
+        # ---- local slices of K_VV + noise I (rows 0..hi are enough: only the upper triangle is read) and of I
+        A = dev.zeros(V, ld)
+        if lo > 0:
+            check(lib.gpx_gram(dev.h, ptr(allpts.X), lo, allpts.ld, ptr(self.pool.X), nloc, ld, ptr(A), ld, 0, None, 0.0, st), "gpx_gram")
+        if nloc > 0:
+            check(lib.gpx_gram(dev.h, ptr(self.pool.X), nloc, ld, ptr(self.pool.X), nloc, ld, ptr(A[lo:]), ld, 1, None,
+                               self.noise, st), "gpx_gram")
+        Y = dev.zeros(V, ld)
+        if nloc > 0:
+            Y[lo:hi, :nloc].fill_diagonal_(1.0)
+        panel = dev.zeros(V, self.BLK)
+        diag = dev.zeros(self.BLK, self.BLK)
+        info = dev.zeros(1, dtype=torch.int32)
+        bad = dev.zeros(1, dtype=torch.int32)
+        group = shard.group if shard is not None else None
+        B = self.BLK
+        for kb in range(0, V, B):
+            b = min(B, V - kb)
+            owner = max(r for r in range(world) if self.bounds[r] <= kb)
+            mine = rank == owner
+            if kb > 0:
+                if mine:
+                    panel[:kb, :b].copy_(A[:kb, kb - lo: kb - lo + b])
+                if world > 1:
+                    dist.broadcast(panel[:kb], src=owner, group=group)
+                cu = max(lo, kb) - lo
+                if nloc - cu > 0:
+                    check(lib.gpx_dgemm_tn_sub(dev.h, ptr(panel), B, ptr(A) + 8 * cu, ld, ptr(A) + 8 * (kb * ld + cu), ld, b,
+                                               nloc - cu, kb, 0, st), "gpx_dgemm_tn_sub")
+                ny = min(hi, kb + b) - lo
+                if ny > 0:
+                    check(lib.gpx_dgemm_tn_sub(dev.h, ptr(panel), B, ptr(Y), ld, ptr(Y) + 8 * kb * ld, ld, b, ny, kb, 0, st),
+                          "gpx_dgemm_tn_sub")
+            if mine:
+                check(lib.gpx_potrf(dev.h, ptr(A) + 8 * (kb * ld + kb - lo), b, ld, ptr(info), st), "gpx_potrf")
+                bad.copy_(torch.maximum(bad, torch.where(info > 0, info + kb, info)))
+                diag[:b, :b].copy_(A[kb: kb + b, kb - lo: kb - lo + b])
+            if world > 1:
+                dist.broadcast(diag, src=owner, group=group)
+            cs = max(lo, kb + b) - lo
+            if nloc - cs > 0:
+                check(lib.gpx_trsm(dev.h, ptr(diag), b, B, ptr(A) + 8 * (kb * ld + cs), nloc - cs, ld, st), "gpx_trsm")
+            ny = min(hi, kb + b) - lo
+            if ny > 0:
+                check(lib.gpx_trsm(dev.h, ptr(diag), b, B, ptr(Y) + 8 * kb * ld, ny, ld, st), "gpx_trsm")
+        if world > 1:
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=group)
+        self.info = bad
+        self.Y = Y
+        del A, panel
+        self.pd = dev.zeros(ld)
+        if nloc > 0:
+            check(lib.gpx_colsumsq(dev.h, ptr(Y), V, nloc, ld, None, ptr(self.pd), st), "gpx_colsumsq")
+        # ---- greedy state
+        self.W = dev.zeros(ncap, ld)
+        self.num = dev.zeros(ld)
+        check(lib.gpx_prior_diag(dev.h, ptr(self.pool.X), nloc, ld, ptr(self.num), st), "gpx_prior_diag")
+        self.Us = dev.zeros(ncap, ld)
+        self.pcol = dev.zeros(ld)
+        self.pws = dev.zeros(max(int(lib.gpx_mi_prec_column_workspace(V, ld)), 1))
+        self.bufY_len = HDR + V
+        self.buf = dev.zeros(self.bufY_len + HDR + ncap)
+        self.loc2 = dev.zeros(2, dtype=torch.int64)
+        self.mask = dev.zeros(ld, dtype=torch.uint8)
+        self.scores = dev.zeros(ld)
+        self.score_trace = None
+
+    def _local_count(self):
+        return self.hi - self.lo
+
+    def score(self):
+        dev = self.dev
+        nloc = self.hi - self.lo
+        check(lib.gpx_score_mi(dev.h, ptr(self.num), ptr(self.pd), self.noise, ptr(self.mask), max(nloc, 1), ptr(self.scores),
+                               ptr(self.best), ptr(self.idx), dev.stream), "gpx_score_mi")
+        dev.launches += 2
+
+    def take(self):
+        dev, pool, ld, V = self.dev, self.pool, self.ld, self.V
+        nloc = self.hi - self.lo
+        st = dev.stream
+        self._gather(self.W, ld, self.num, pool, self.noise, minimize=False)
+        check(lib.gpx_append_row(dev.h, _lib.ROW_KERNEL, ptr(self.rec_win), None, ptr(pool.X), nloc, ld, ptr(self.W), ld,
+                                 self.n, ptr(self.num), st), "gpx_append_row")
+        check(lib.gpx_local_index(dev.h, ptr(self.rec_win), self.lo, nloc, ptr(self.loc2), st), "gpx_local_index")
+        self.buf.zero_()
+        bufY, bufU = self.buf[: self.bufY_len], self.buf[self.bufY_len:]
+        check(lib.gpx_gather_column(dev.h, ptr(self.Y), ld, V, ptr(self.pd), ptr(self.loc2), ptr(bufY), st), "gpx_gather_column")
+        check(lib.gpx_gather_column(dev.h, ptr(self.Us), ld, self.n, ptr(self.pd), ptr(self.loc2), ptr(bufU), st),
+              "gpx_gather_column")
+        if self.rec_all is not None:
+            self.dist.all_reduce(self.buf, op=self.dist.ReduceOp.SUM, group=self.shard.group)
+        check(lib.gpx_mi_prec_column(dev.h, ptr(self.Y), V, nloc, ld, self.lo, ptr(self.loc2) + 8, ptr(bufY) + 8 * HDR,
+                                     ptr(self.pws), ptr(self.pcol), st), "gpx_mi_prec_column")
+        check(lib.gpx_append_row(dev.h, _lib.ROW_MATRIX, ptr(bufU), ptr(self.pcol), None, nloc, ld, ptr(self.Us), ld, self.n,
+                                 ptr(self.pd), st), "gpx_append_row")
+        check(lib.gpx_set_mask(dev.h, ptr(self.mask), ptr(self.loc2), 1, st), "gpx_set_mask")
+        dev.launches += 9
+        self._record()
+        self.n += 1
+
+    def force(self, index: int):
+        self._force_local(int(index))
+        self.take()
+
+    def step(self):
+        self.score()
+        if self.score_trace is not None:
+            self.score_trace.append(self.scores[: self.hi - self.lo].cpu().numpy().copy())
         self.take()
 
     def run(self, n_points: int, start: int = 0):

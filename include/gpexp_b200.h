@@ -183,11 +183,22 @@ int gpx_score_ivar(gpx_handle h, const double* Wm, int64_t ldm, const double* va
 int gpx_score_mi(gpx_handle h, const double* num_var, const double* prec_diag, double noise, const uint8_t* mask,
                  int64_t n, double* score_out, double* best, int64_t* idx, void* stream);
 
-/* K6  column p of P = Y^T Y for the lower-triangular Y = U^-T (row-major):  out[i] = sum_k Y[k,i] Y[k,p].
- *     workspace: gpx_mi_prec_column_workspace(n, ldy) doubles (row-chunk partials, added in a fixed order). */
-int64_t gpx_mi_prec_column_workspace(int64_t n, int64_t ldy);
-int gpx_mi_prec_column(gpx_handle h, const double* Y, int64_t n, int64_t ldy, const int64_t* p_dev, double* workspace,
-                       double* out, void* stream);
+/* K6  column p of P = Y^T Y for the lower-triangular Y = U^-T:  out[i] = sum_{k >= max(i,p)} Y[k,i] Y[k,p].
+ *     Y is nrows x ncols (row-major): the whole matrix (col_offset = 0, ncols = nrows, ycol = NULL) or the column slice
+ *     [col_offset, col_offset+ncols) owned by this rank, in which case column p arrives as the dense vector ycol[nrows]
+ *     (all-reduced from its owner).  *p_dev is the GLOBAL index.  workspace: gpx_mi_prec_column_workspace doubles. */
+int64_t gpx_mi_prec_column_workspace(int64_t nrows, int64_t ldy);
+int gpx_mi_prec_column(gpx_handle h, const double* Y, int64_t nrows, int64_t ncols, int64_t ldy, int64_t col_offset,
+                       const int64_t* p_dev, const double* ycol, double* workspace, double* out, void* stream);
+
+/* Sharded pools: copy column *idx_dev of W (n rows) into rec[GPX_PIVOT_HDR..] and var[*idx_dev] into rec[2];
+ * nothing is written when *idx_dev < 0, so zeroed records can be summed across ranks (owner contributes). */
+int gpx_gather_column(gpx_handle h, const double* W, int64_t ldw, int64_t n, const double* var, const int64_t* idx_dev,
+                      double* rec, void* stream);
+
+/* out2[0] = local index of the pivot in rec (global index rec[1]) for the block [offset, offset+count), or -1;
+ * out2[1] = the global index. */
+int gpx_local_index(gpx_handle h, const double* rec, int64_t offset, int64_t count, int64_t* out2, void* stream);
 
 /* Column sums of squares: out[j] = sum_{i<n} W[i,j]^2 (optionally out[j] = base[j] - that). */
 int gpx_colsumsq(gpx_handle h, const double* W, int64_t n, int64_t ncols, int64_t ldw, const double* base,

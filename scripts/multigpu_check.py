@@ -37,18 +37,31 @@ def main():
     lo, hi = Shard.split(pool.shape[0], world, rank)
     eng = GreedyVarEngine(dev, dev.points(pool[lo:hi]), 25, shard=shard, index_offset=lo)
     vidx = eng.run(25)
+    # --- greedy mutual information, |V| x |V| matrices sharded by column blocks ------------------------
+    from gpexp_b200.engine import ShardedMIEngine
+    vpool = rng.standard_normal((1500, 3))
+    hk = kernels.KernelMehlerND([0.9, 0.9, 0.9], 3)
+    hk._bind(dev)
+    meng = ShardedMIEngine(dev, vpool, 14, 1e-2, shard=shard)
+    midx = meng.run(14, start=0)
+    minfo = int(meng.info.item())
     torch.cuda.synchronize()
     if rank == 0:
         from oracle import gpexp_oracle as orc
+        mref, _ = orc.fast_greedy_mi(orc.KernelSpec.mehler([0.9, 0.9, 0.9], 3), vpool, 1e-2, 14, start=0)
+        mi_ok = [int(i) for i in midx] == mref and minfo == 0
+        print("multigpu_check world=%d mi=%s -> %s" % (world, [int(i) for i in midx][:8], "OK" if mi_ok else "MISMATCH"), flush=True)
+        if not mi_ok:
+            print("ref mi", mref, "got", [int(i) for i in midx], "info", minfo)
         ref, _ = orc.fast_greedy_ivar(orc.KernelSpec.se([0.2, 0.3], 1.0, 2), cand, mc, 12, 1e-6)
         vref, _ = orc.fast_greedy_var(orc.KernelSpec.matern32(1.0, 1.0, 5), pool, 25)
-        ok = [int(i) for i in idx] == ref and [int(i) for i in vidx] == vref
+        ok = [int(i) for i in idx] == ref and [int(i) for i in vidx] == vref and mi_ok
         print("multigpu_check world=%d ivar=%s var=%s -> %s" % (world, [int(i) for i in idx][:6], [int(i) for i in vidx][:6],
                                                                  "OK" if ok else "MISMATCH"), flush=True)
         if not ok:
             print("ref ivar", ref, "got", [int(i) for i in idx]); print("ref var", vref, "got", [int(i) for i in vidx])
     # every rank must hold the same picks
-    t = torch.tensor([int(i) for i in idx] + [int(i) for i in vidx], device="cuda")
+    t = torch.tensor([int(i) for i in idx] + [int(i) for i in vidx] + [int(i) for i in midx], device="cuda")
     g = [torch.zeros_like(t) for _ in range(world)]
     dist.all_gather(g, t)
     same = all(bool((x == t).all()) for x in g)

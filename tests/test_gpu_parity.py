@@ -263,7 +263,7 @@ def test_potrf_trsm_blocks(gx, n):
     p = dev.upload(np.array([n // 2], dtype=np.int64), dtype=gx.torch.int64)
     col = dev.zeros(ld)
     ws = dev.zeros(max(int(lib.gpx_mi_prec_column_workspace(n, ld)), 1))
-    gx.check(lib.gpx_mi_prec_column(dev.h, ptr(Y), n, ld, ptr(p), ptr(ws), ptr(col), dev.stream))
+    gx.check(lib.gpx_mi_prec_column(dev.h, ptr(Y), n, n, ld, 0, ptr(p), None, ptr(ws), ptr(col), dev.stream))
     np.testing.assert_allclose(col[:n].cpu().numpy(), np.linalg.inv(A)[:, n // 2], rtol=1e-7, atol=1e-9)
     # rank-1 append reproduces the factor of the bordered matrix
     if n >= 2:
@@ -487,3 +487,23 @@ def test_cfg5_shape_step_vs_oracle_subset(gx):
     ref = orc.fast_ivar_scores(ks, cand[sub], mc, w_m, var_m, w_c, var_c, 1e-6)
     assert np.max(np.abs(costs[sub] - ref) / np.abs(ref)) <= 1e-9
     assert costs[best] == costs.min()
+
+
+def test_sharded_mi_engine_single_rank_equals_dense_engine(gx):
+    """The column-sharded MI engine (left-looking blocked factorisation, Y = U^-T built block row by block row)
+    run with one rank must reproduce the dense engine and the oracle; the 2- and 8-rank runs are covered by
+    scripts/multigpu_check.py."""
+    rng = np.random.default_rng(21)
+    for name, V, N, noise in [("mehler_3d", 700, 10, 1e-2), ("matern_5d", 1000, 8, 1e-3)]:
+        ks = spec(name)
+        bind(gx, name)
+        pool = rng.standard_normal((V, ks.dim)) if name.startswith("mehler") else rng.uniform(-1, 1, (V, ks.dim))
+        ref, ref_scores = orc.fast_greedy_mi(ks, pool, noise, N, start=2)
+        eng = gx.engine.ShardedMIEngine(gx.dev, pool, N, noise)
+        eng.score_trace = []
+        idx = eng.run(N, start=2)
+        assert int(eng.info.item()) == 0
+        assert [int(i) for i in idx] == ref, name
+        for s, sc in enumerate(eng.score_trace):
+            ok = np.isfinite(ref_scores[s])
+            assert np.max(np.abs(sc[ok] - ref_scores[s][ok]) / np.abs(ref_scores[s][ok])) <= 1e-8
