@@ -19,7 +19,8 @@ import numpy as np
 from . import _lib
 from ._lib import check, lib
 from .device import Device, ptr
-from .engine import (DesignFactor, GreedyIVAREngine, GreedyMIEngine, GreedyVarEngine, Shard, prior_scale)
+from .engine import (DesignFactor, GreedyIVAREngine, GreedyMIEngine, GreedyVarEngine, Shard, ShardedMIEngine,
+                     prior_scale)
 from .gp_kernel_utilities import _nugget_arg
 
 VERBOSE = True  # the reference prints its progress unconditionally (experimentalDesign.py:812-813)
@@ -129,11 +130,19 @@ class costFunctionGP_MI(costFunctionBase):
         return eng.scores[int(index): int(index) + 1].cpu().numpy()
 
 
-def performGreedyMIExperimentalDesign(costFuncMI, nPoints, start=0):
+def performGreedyMIExperimentalDesign(costFuncMI, nPoints, start=0, shard=None):
     """Greedy MI design over the cost function's pool (experimentalDesign.py:753-785).
     Returns the chosen POINTS (as the reference does); the indices are left in
-    `costFuncMI.lastIndices`."""
-    eng = costFuncMI._new_engine(nPoints)
+    `costFuncMI.lastIndices`.  With `shard` (gpexp_b200.engine.Shard, every rank passing the same pool) the
+    |V| x |V| factorisation is column-sharded over the ranks (ShardedMIEngine) -- required above |V| ~ 9e4."""
+    if shard is not None:
+        gp = costFuncMI.gaussianProcess
+        noise = _nugget_arg(gp.noise)
+        if isinstance(noise, np.ndarray):
+            raise NotImplementedError("MI with per-point noise is not supported on the device path")
+        eng = ShardedMIEngine(gp.kernel._bind(), costFuncMI.mcPoints, nPoints, float(noise), shard=shard)
+    else:
+        eng = costFuncMI._new_engine(nPoints)
     idx = eng.run(nPoints, start=start)
     costFuncMI.lastIndices = idx
     costFuncMI._engine = eng

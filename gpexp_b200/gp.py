@@ -37,9 +37,21 @@ class GP:
         self.noise = noiseIn
         if 'FITC' in kwargs and kwargs['FITC'] is not None:
             raise NotImplementedError("FITC sparse GPs are outside the B200 hot path (gp.py:182-208)")
-        self._factor = None
+        self._factor_obj = None
+        self._pending = None
         self._cov_host = None
         self._prec_host = None
+
+    # The Gram matrix and its Cholesky factor are built on first use (a costFunctionGP_MI over a pool that only the
+    # column-sharded engine can hold must not force a dense |V| x |V| factor on one GPU at construction time).
+    @property
+    def _factor(self):
+        if self._factor_obj is None and self._pending is not None:
+            nodes, nugget = self._pending
+            dev = self.kernel._bind()
+            self._factor_obj = DesignFactor(dev, dev.points(nodes), nugget)
+            self._pending = None
+        return self._factor_obj
 
     # covarianceMatrix / precisionMatrix are materialised on the host only when somebody reads them
     @property
@@ -82,9 +94,9 @@ class GP:
     def addNodesAndComputeCovariance(self, nodes, noiseIn=None):
         """Gram + Cholesky of the design (gp.py:156-211, non-FITC branch)."""
         nugget = _nugget_arg(self.noise if noiseIn is None else noiseIn)
-        dev = self.kernel._bind()
-        design = dev.points(nodes)
-        self._factor = DesignFactor(dev, design, nugget)
+        self.kernel._bind()  # fails loudly here if there is no device / library
+        self._factor_obj = None
+        self._pending = (nodes.copy(), nugget.copy() if isinstance(nugget, np.ndarray) else nugget)
         self._cov_host = None
         self._prec_host = None
         self.pts = nodes.copy()

