@@ -432,7 +432,7 @@ __device__ __forceinline__ void bulk_g2s(double* dst, const double* src, unsigne
                  : "memory");
 }
 
-template <int FAM, bool DB>
+template <int FAM>
 __global__ void __launch_bounds__(WS_THREADS, 1)
     ivar_ws_kernel(const __grid_constant__ CoreArgs a, const __grid_constant__ KParams kp) {
     constexpr int BM = WS_BM, LD = WS_LD;
@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
     {
         // ================= consumer warps ===========================================================
         double acc[4][8][2];
-        double af0[4], bf0[8], af1[4], bf1[8];
+        double af0[4], bf0[8];
         const int fa = q4 * LD + wm * 32 + g4 * 2;
         const int fb = BK * LD + q4 * LD + wn * 64 + g4 * 2;
         int tl = 0, ch = 0;
@@ -551,21 +551,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
                 const int rem = a.K - (ch - 1) * BK;
                 ksteps = rem >= BK ? 4 : ((rem + 3) >> 2);
             }
-            if (DB && ksteps == 4) {
-                load_frags<LD, LD>(af0, bf0, pa, pb, 0);
-                load_frags<LD, LD>(af1, bf1, pa, pb, 1);
-                mma_tile(acc, af0, bf0);
-                load_frags<LD, LD>(af0, bf0, pa, pb, 2);
-                mma_tile(acc, af1, bf1);
-                load_frags<LD, LD>(af1, bf1, pa, pb, 3);
-                mma_tile(acc, af0, bf0);
-                mma_tile(acc, af1, bf1);
-            } else {
+            // single-buffered fragments: the other warp of the sub-partition covers the LDS latency (double
+            // buffering measured identical: 34.44 vs 34.43 TFLOP/s at n = 4095)
 #pragma unroll 1
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    load_frags<LD, LD>(af0, bf0, pa, pb, ks);
-                    mma_tile(acc, af0, bf0);
-                }
+            for (int ks = 0; ks < ksteps; ++ks) {
+                load_frags<LD, LD>(af0, bf0, pa, pb, ks);
+                mma_tile(acc, af0, bf0);
             }
             if (ch == 0) {
                 // covariance from the expanded form; accumulators become -k so that the main loop yields T - k
@@ -653,32 +644,19 @@ bool ivar_use_tma() {
     }
     return v == 1;
 }
-bool ivar_double_buffer() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("GPX_IVAR_DB");
-        v = (e && e[0] == '1') ? 1 : 0;
-    }
-    return v == 1;
-}
-
-template <int FAM, bool DB>
-int launch_ivar_ws_db(const CoreArgs& a, const KParams& kp, dim3 grid, cudaStream_t st) {
+template <int FAM>
+int launch_ivar_ws(const CoreArgs& a, const KParams& kp, dim3 grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(ivar_ws_kernel<FAM, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(ivar_ws_kernel<FAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES);
         if (e != cudaSuccess) {
             gpx_set_error("ivar_ws: cannot opt in to %zu bytes of shared memory: %s", WS_SMEM_BYTES, cudaGetErrorString(e));
             return (int)e;
         }
         configured = true;
     }
-    ivar_ws_kernel<FAM, DB><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(a, kp);
+    ivar_ws_kernel<FAM><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(a, kp);
     return gpx_check_launch("ivar_ws");
-}
-template <int FAM>
-int launch_ivar_ws(const CoreArgs& a, const KParams& kp, dim3 grid, cudaStream_t st) {
-    return ivar_double_buffer() ? launch_ivar_ws_db<FAM, true>(a, kp, grid, st) : launch_ivar_ws_db<FAM, false>(a, kp, grid, st);
 }
 
 // tile shape used by every launch: GPX_WM=2 (64x128, 2 CTAs/SM) or 4 (128x128, 1 CTA/SM)
@@ -716,7 +694,7 @@ int launch_core(const CoreArgs& a, const KParams& kp, int64_t jt, int64_t it_or_
 }
 
 int core_bm() { return core_wm() * 32; }
-int ivar_bm() { return ivar_use_tma() ? WS_BM : core_bm(); }
+
 
 int check_operand(const double* p, int64_t ld, const char* name) {
     if (!gpx_aligned16(p) || (ld & 1)) {
@@ -729,9 +707,9 @@ int check_operand(const double* p, int64_t ld, const char* name) {
 }  // namespace
 
 // number of i-splits for the IVAR grid: fill the machine in whole waves
-int gpx_ivar_splits(gpx_handle h, int64_t M, int64_t C) {
+static int ivar_splits_for(gpx_handle h, int64_t M, int64_t C, int bm) {
     const int64_t jt = (C + BN - 1) / BN;
-    const int64_t itl = (M + ivar_bm() - 1) / ivar_bm();
+    const int64_t itl = (M + bm - 1) / bm;
     const int sms = h->sm_count > 0 ? h->sm_count : 148;
     int best = 1;
     double best_eff = -1.0;
@@ -750,6 +728,7 @@ int gpx_ivar_splits(gpx_handle h, int64_t M, int64_t C) {
     }
     return best;
 }
+int gpx_ivar_splits(gpx_handle, int64_t, int64_t) { return 32; }  // workspace bound: never more than 32 splits
 
 int gpx_launch_core_ivar(gpx_handle h, const double* Wm, int64_t ldm, const double* Ma_rows, const double* Ma_scal,
                          int64_t M, const double* Wc, int64_t ldc, const double* Cb_rows, const double* Cb_scal,
@@ -761,8 +740,14 @@ int gpx_launch_core_ivar(gpx_handle h, const double* Wm, int64_t ldm, const doub
         if ((rc = check_operand(Wm, ldm, "Wm"))) return rc;
         if ((rc = check_operand(Wc, ldc, "Wc"))) return rc;
     }
-    const int splits = gpx_ivar_splits(h, M, C);
-    const int64_t itl = (M + ivar_bm() - 1) / ivar_bm();
+    // the TMA path reads whole 128-wide tiles: operands must be padded to full tiles (the engines do that);
+    // anything else goes through the predicated cp.async core
+    const bool padded = (ldm % WS_BM) == 0 && (ldc % BN) == 0 && ldm >= (M + WS_BM - 1) / WS_BM * WS_BM &&
+                        ldc >= (C + BN - 1) / BN * BN;
+    const bool tma = ivar_use_tma() && padded;
+    const int bm = tma ? WS_BM : core_bm();
+    const int splits = ivar_splits_for(h, M, C, bm);
+    const int64_t itl = (M + bm - 1) / bm;
     CoreArgs a;
     a.A = Wm;
     a.B = Wc;
@@ -781,14 +766,7 @@ int gpx_launch_core_ivar(gpx_handle h, const double* Wm, int64_t ldm, const doub
     a.tiles_per_cta = (int)((itl + splits - 1) / splits);
     a.upper_only = 0;
     *nsplit_out = splits;
-    // the TMA path reads whole 128-wide tiles: operands must be padded to full tiles
-    const bool padded = (ldm % WS_BM) == 0 && (ldc % BN) == 0 && ldm >= (M + WS_BM - 1) / WS_BM * WS_BM &&
-                        ldc >= (C + BN - 1) / BN * BN;
-    if (ivar_use_tma()) {
-        if (!padded) {
-            gpx_set_error("gpx_score_ivar: leading dimensions must be multiples of 128 covering whole tiles");
-            return GPX_EALIGN;
-        }
+    if (tma) {
         dim3 grid((unsigned)((C + BN - 1) / BN), (unsigned)splits);
         GPX_DISPATCH_FAMILY(h->kp.family, rc = (launch_ivar_ws<FAM>(a, h->kp, grid, st)));
         return rc;

@@ -507,3 +507,90 @@ def test_sharded_mi_engine_single_rank_equals_dense_engine(gx):
         for s, sc in enumerate(eng.score_trace):
             ok = np.isfinite(ref_scores[s])
             assert np.max(np.abs(sc[ok] - ref_scores[s][ok]) / np.abs(ref_scores[s][ok])) <= 1e-8
+
+
+# ------------------------------------------------------------------------------------------------
+# limits and error behaviour of the C ABI
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", [13, 16])
+def test_max_dimension_ivar_and_gram(gx, d):
+    """GPX_MAX_DIM = 16: the Gram prologue then fills the whole 16-row K chunk (d = 13 pads to 16)."""
+    from gpexp_b200 import kernels as K
+    rng = np.random.default_rng(d)
+    cl = list(np.linspace(0.8, 2.0, d))
+    ks = orc.KernelSpec.se(cl, 1.3, d)
+    k = K.KernelSquaredExponential(cl, 1.3, d)
+    cand, mc, design = rng.uniform(-1, 1, (700, d)), rng.uniform(-1, 1, (900, d)), rng.uniform(-1, 1, (37, d))
+    np.testing.assert_allclose(gx.gku.calculateCovarianceMatrix(k, design, 1e-6), ks.gram(design, design).T + 1e-6 * np.eye(37),
+                               rtol=RTOL_K)
+    w_m, var_m = orc.fast_design_state(ks, design, mc, 1e-6)
+    w_c, var_c = orc.fast_design_state(ks, design, cand, 1e-6)
+    ref = orc.fast_ivar_scores(ks, cand, mc, w_m, var_m, w_c, var_c, 1e-6)
+    cf = gx.ed.costFunctionGP_IVAR(gx.gp.GP(k, 1e-6), 1, gx.Space(d, None, None), mcPoints=mc)
+    costs, best = gx.ed.scoreCandidatesIVAR(cf, design, cand)
+    assert best == int(np.argmin(ref)) and np.max(np.abs(costs - ref) / np.abs(ref)) <= 1e-9
+    with pytest.raises(gx._lib.GpxError):
+        K.KernelSquaredExponential([1.0], 1.0, 17).evaluate(np.zeros((2, 17)), np.zeros((2, 17)))
+
+
+def test_c_abi_error_codes(gx):
+    dev, lib, ptr, torch = gx.dev, gx.lib, gx.ptr, gx.torch
+    bind(gx, "se_ard_2d")
+    a = dev.zeros(4, 130)
+    info = dev.zeros(1, dtype=torch.int32)
+    # odd leading dimension / misaligned pointer -> GPX_EALIGN, message available, nothing launched
+    assert lib.gpx_potrf(dev.h, ptr(a), 4, 129, ptr(info), dev.stream) == -2
+    assert "16-byte" in gx._lib.last_error()
+    assert lib.gpx_dgemm_tn_sub(dev.h, ptr(a) + 8, 130, ptr(a), 130, ptr(a), 130, 2, 2, 2, 0, dev.stream) == -2
+    # bad arguments -> GPX_EINVAL
+    assert lib.gpx_kernel_pairwise(dev.h, ptr(a), 3, 130, ptr(a), 5, 130, ptr(a), dev.stream) == -1
+    assert lib.gpx_gram(dev.h, ptr(a), 2, 130, ptr(a), 200, 130, ptr(a), 130, 0, None, 0.0, dev.stream) == -1  # ld < ny
+    assert lib.gpx_argreduce(dev.h, ptr(a), None, None, -1, 0, ptr(a), ptr(info), dev.stream) == -1
+    # a fresh handle has no kernel -> GPX_ENOKERNEL
+    h2 = C.c_void_p()
+    assert lib.gpx_create(dev.index, C.byref(h2)) == 0
+    assert lib.gpx_prior_diag(h2, ptr(a), 4, 130, ptr(a), dev.stream) == -3
+    import ctypes
+    bad = (ctypes.c_double * 3)(0.5, 0.5, 1.0)
+    assert lib.gpx_set_kernel(h2, 7, 2, bad, 3) == -1           # unknown family
+    assert lib.gpx_set_kernel(h2, 0, 17, bad, 18) == -4          # dimension above GPX_MAX_DIM
+    assert lib.gpx_set_kernel(h2, 2, 2, (ctypes.c_double * 2)(0.5, 1.0), 2) == -1  # Mehler |t| >= 1
+    assert lib.gpx_destroy(h2) == 0
+    # empty inputs are no-ops that succeed
+    assert lib.gpx_gram(dev.h, ptr(a), 0, 130, ptr(a), 0, 130, ptr(a), 130, 0, None, 0.0, dev.stream) == 0
+    assert lib.gpx_append_row(dev.h, 0, ptr(a), None, ptr(a), 0, 130, ptr(a), 130, 0, ptr(a), dev.stream) == 0
+    from gpexp_b200 import kernels as K
+    assert K.KernelSquaredExponential([0.5], 1.0, 2).evaluate(np.zeros((0, 2)), np.zeros((0, 2))).shape == (0,)
+
+
+def test_score_ivar_unpadded_operands_use_the_generic_core(gx):
+    """Raw C-ABI call with leading dimensions that are NOT multiples of 128: gpx_score_ivar must fall back from the
+    TMA kernel (whole-tile reads) to the predicated cp.async core and give the same scores."""
+    dev, lib, ptr, torch = gx.dev, gx.lib, gx.ptr, gx.torch
+    rng = np.random.default_rng(33)
+    ks = spec("matern_5d")
+    bind(gx, "matern_5d")
+    M, Cn, n, noise = 301, 203, 21, 1e-4
+    mc, cand, design = rng.uniform(-1, 1, (M, 5)), rng.uniform(-1, 1, (Cn, 5)), rng.uniform(-1, 1, (n, 5))
+    w_m, var_m = orc.fast_design_state(ks, design, mc, noise)
+    w_c, var_c = orc.fast_design_state(ks, design, cand, noise)
+    ref = orc.fast_ivar_scores(ks, cand, mc, w_m, var_m, w_c, var_c, noise)
+    ldm, ldc = 302, 204
+
+    def up(a, ld):
+        t = dev.zeros(a.shape[0], ld)
+        t[:, : a.shape[1]] = dev.upload(a)
+        return t
+    Xm, Xc = up(mc.T.copy(), ldm), up(cand.T.copy(), ldc)
+    Wm, Wc = up(w_m, ldm), up(w_c, ldc)
+    vM, vC = up(var_m[None, :], ldm), up(var_c[None, :], ldc)
+    ma_rows, ma_s, cb_rows, cb_s = dev.zeros(16, ldm), dev.zeros(ldm), dev.zeros(16, ldc), dev.zeros(ldc)
+    gx.check(lib.gpx_prep_side(dev.h, 0, ptr(Xm), M, ldm, ptr(ma_rows), ptr(ma_s), ldm, dev.stream))
+    gx.check(lib.gpx_prep_side(dev.h, 1, ptr(Xc), Cn, ldc, ptr(cb_rows), ptr(cb_s), ldc, dev.stream))
+    ws = dev.zeros(int(lib.gpx_score_ivar_workspace(dev.h, M, Cn)))
+    score, best, idx = dev.zeros(ldc), dev.zeros(1), dev.zeros(1, dtype=torch.int64)
+    gx.check(lib.gpx_score_ivar(dev.h, ptr(Wm), ldm, ptr(vM), ptr(ma_rows), ptr(ma_s), M, ptr(Wc), ldc, ptr(vC), ptr(cb_rows),
+                                ptr(cb_s), Cn, n, noise, 1e-13, None, ptr(ws), ptr(score), ptr(best), ptr(idx), dev.stream))
+    got = score[:Cn].cpu().numpy()
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-9
+    assert int(idx.item()) == int(np.argmin(ref)) and best.item() == got.min()
