@@ -70,6 +70,10 @@ SIGNATURES = {
     "gpx_transpose": [_p, _p, _i64, _i64, _i64, _p, _i64, _p],
     "gpx_set_mask": [_p, _p, _p, C.c_uint8, _p],
     "gpx_store_pivot": [_p, _p, _i64, _p, _i64, _p, _p, _p],
+    "gpx_se_dgram": [_p, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p],
+    "gpx_se_var_grad": [_p, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _p],
+    "gpx_rowsum": [_p, _p, _i64, _i64, _i64, _dbl, _p, _p],
+    "gpx_logdet_chol": [_p, _p, _i64, _i64, _p, _p],
     "gpx_bench_dmma": [_p, _i64, _p, _p],
     "gpx_bench_dfma": [_p, _i64, _p, _p],
 }

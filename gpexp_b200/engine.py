@@ -229,6 +229,43 @@ class DesignFactor:
         check(lib.gpx_trsm_back(dev.h, ptr(self.Ut()), self.n, self.ldu, ptr(B), 1, 2, dev.stream), "gpx_trsm_back")
         return B[: self.n, 0].cpu().numpy()
 
+    def logdet(self) -> float:
+        """log det(K + nugget) = 2 sum log U_ii."""
+        dev = self.dev
+        out = dev.zeros(1)
+        check(lib.gpx_logdet_chol(dev.h, ptr(self.U), self.n, self.ldu, ptr(out), dev.stream), "gpx_logdet_chol")
+        dev.launches += 1
+        return float(out.item())
+
+    def whitened_norm2(self, y: np.ndarray) -> float:
+        """|U^-T y|^2 = y^T (K + nugget)^-1 y."""
+        dev = self.dev
+        B = dev.zeros(max(self.n, 1), 2)
+        B[: self.n, 0] = dev.upload(np.asarray(y, dtype=np.float64))
+        check(lib.gpx_trsm(dev.h, ptr(self.U), self.n, self.ldu, ptr(B), 1, 2, dev.stream), "gpx_trsm")
+        out = dev.zeros(2)
+        check(lib.gpx_colsumsq(dev.h, ptr(B), self.n, 1, 2, None, ptr(out), dev.stream), "gpx_colsumsq")
+        return float(out[0].item())
+
+    def variance_gradient(self, X: PointSet):
+        """(n*d) x X.ld device matrix  out[j*d+k, m] = d var(x_m) / d design[j,k]  as GP.evaluateVarianceDerivative
+        (gp.py:282-341) defines it.  Squared-exponential kernels only."""
+        dev, D = self.dev, self.design
+        n, d = self.n, D.d
+        W, _ = self.solve_gram(X, want_var=False)
+        check(lib.gpx_trsm_back(dev.h, ptr(self.Ut()), n, self.ldu, ptr(W), X.n, X.ld, dev.stream), "gpx_trsm_back")  # At = P K(D,X)
+        ldn = roundup(n * d)
+        dct = dev.zeros(max(n, 1), ldn)
+        check(lib.gpx_se_dgram(dev.h, ptr(D.X), n, D.ld, ptr(D.X), n, D.ld, ptr(dct), ldn, dev.stream), "gpx_se_dgram")
+        qneg = dev.zeros(max(n * d, 1), X.ld)
+        check(lib.gpx_dgemm_tn_sub(dev.h, ptr(dct), ldn, ptr(W), X.ld, ptr(qneg), X.ld, n * d, X.n, n, 0, dev.stream),
+              "gpx_dgemm_tn_sub")
+        out = dev.zeros(max(n * d, 1), X.ld)
+        check(lib.gpx_se_var_grad(dev.h, ptr(D.X), n, D.ld, ptr(X.X), X.n, X.ld, ptr(W), ptr(qneg), ptr(out), dev.stream),
+              "gpx_se_var_grad")
+        dev.launches += 4 + 2 * ((n + 127) // 128)
+        return out
+
     def precision(self) -> np.ndarray:
         """(U^T U)^-1 as a dense matrix: U^-1 (U^-T I)."""
         dev, n = self.dev, self.n

@@ -77,6 +77,26 @@ class costFunctionGP_IVAR(costFunctionBase):
         return np.abs(cost)
 
 
+    def derivative(self, inputPoints):
+        """Gradient of the IVAR cost with respect to the design coordinates, shape (nPoints*dimension,)
+        (experimentalDesign.py:148-179, version 1): the row mean over the MC points of
+        GP.evaluateVarianceDerivative.  Squared-exponential kernels, homoscedastic noise."""
+        if self.space.noiseFunc is not None:
+            raise NotImplementedError("the heteroscedastic IVAR gradient is not on the device path")
+        gp = self.gaussianProcess
+        gp.kernel._require_derivative()
+        gp.addNodesAndComputeCovariance(inputPoints)
+        f = gp._factor
+        mc = self._mc_points(f.dev)
+        full = f.variance_gradient(mc)
+        rows = f.n * gp.kernel.dimension
+        out = f.dev.zeros(max(rows, 1))
+        check(lib.gpx_rowsum(f.dev.h, ptr(full), rows, mc.n, mc.ld, 1.0 / float(self.nMC), ptr(out), f.dev.stream),
+              "gpx_rowsum")
+        f.dev.launches += 1
+        return out[:rows].cpu().numpy()
+
+
 class costFunctionGP_MI(costFunctionBase):
     """Krause-Guestrin mutual-information ratio var(y|A) / var(y|V minus A minus y)."""
 

@@ -123,6 +123,48 @@ class GP:
         _, X, _, var = self._variance_device(newpt)
         return var[: X.n].cpu().numpy()
 
+    def evaluateVarianceDerivative(self, newpt, noiseFunc=None):
+        """Posterior-variance derivative with respect to the training points (gp.py:282-341):
+        out[k*l, jj] = dC(newpt[jj], newpt[jj]) / d self.pts[k, l], shape (len(pts)*dim, len(newpt)).
+        Squared-exponential kernels only (the reference has no ND derivative for the other families)."""
+        assert self.pts is not None, "must specify training points before running this"
+        assert newpt.shape[1] == self.kernel.dimension, "evaluation points for GP is incorrect shape"
+        if noiseFunc is not None:
+            raise NotImplementedError("the heteroscedastic variance derivative is not on the device path")
+        self.kernel._require_derivative()
+        f = self._require_factor()
+        X = f.dev.points(newpt)
+        out = f.variance_gradient(X)
+        return out[: f.n * self.kernel.dimension, : X.n].cpu().numpy()
+
+    def computeLogLike(self, pts, evals):
+        """Marginal log-likelihood of (pts, evals) under the current hyper-parameters (gp.py:373-392)."""
+        return self.loglikeParams(pts, evals)
+
+    def loglikeParams(self, pts, evals, returnDeriv=0, noiseIn=None):
+        """-1/2 y^T K^-1 y - 1/2 log|K| - n/2 log 2 pi with K = Gram + noise (gp.py:394-446), through the device
+        Cholesky factor.  The hyper-parameter gradient (returnDeriv=1, gp.py:447-468) is not on the device path."""
+        if returnDeriv:
+            raise NotImplementedError("hyper-parameter gradients of the log-likelihood are outside the B200 path")
+        nugget = _nugget_arg(self.noise if noiseIn is None else noiseIn)
+        dev = self.kernel._bind()
+        f = DesignFactor(dev, dev.points(pts), nugget)
+        first = -0.5 * f.whitened_norm2(evals)
+        second = -0.5 * f.logdet()
+        third = -len(evals) / 2.0 * np.log(2.0 * np.pi)
+        return first + second + third
+
+    def getHypParamNames(self):
+        return self.kernel.hyperParam.keys()
+
+    def updateKernelParams(self, paramsIn):
+        """Set new hyper-parameters; a 'noise' entry updates the GP noise (gp.py:474-497)."""
+        params = copy.copy(paramsIn)
+        if 'noise' in params.keys():
+            self.noise = copy.copy(params['noise'])
+            del params['noise']
+        self.kernel.updateHyperParameters(params)
+
     def evaluate(self, newpt, compvar=0):
         """Posterior mean, and variance (compvar=1, abs'd as gp.py:145) or covariance (compvar=2)."""
         assert newpt.shape[1] == self.kernel.dimension, "evaluation points for GP is incorrect shape"

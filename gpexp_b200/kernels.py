@@ -41,6 +41,10 @@ class Kernel(object):
         dev.set_kernel(fam, d, params)
         return dev
 
+    def _require_derivative(self):
+        """Only KernelSquaredExponential has an N-D `derivative` in the reference."""
+        raise AttributeError("derivative of %s not implemented" % type(self).__name__)
+
     def evaluate(self, x1, x2):
         assert len(x2.shape) > 1 and len(x1.shape) > 1, "Must supply nd arrays to evaluation function"
         nPointsx1 = x1.shape[0]
@@ -96,6 +100,24 @@ class KernelSquaredExponential(Kernel):
     def _gpx_spec(self):
         cl = [self.hyperParam['cl' + str(ii)] for ii in range(self.dimension)]
         return _lib.SE, self.dimension, cl + [self.hyperParam['signalSize']]
+
+    def _require_derivative(self):
+        return True
+
+    def derivative(self, x1, x2, version=0):
+        """out[jj, ii] = dK(x1[jj], x2)/dx1[jj, ii] as the reference computes it (kernels.py:146-181):
+        -signalSize * (x1 - x2)/cl^2 * evaluate(x1, x2).  x2 is a single (1, d) point."""
+        assert len(x2.shape) > 1 and len(x1.shape) > 1, "Must supply nd arrays to evaluation function"
+        assert x2.shape[0] == 1 and x2.shape[1] == self.dimension, "x2 not in correct shape"
+        assert x1.shape[0] > 0 and x1.shape[1] == self.dimension, "x1 not in correct shape"
+        dev = self._bind()
+        a, b = dev.points(x1), dev.points(x2)
+        n, d = x1.shape
+        ld = max(n * d, 1)
+        out = dev.zeros(1, ld)
+        check(lib.gpx_se_dgram(dev.h, ptr(b.X), 1, b.ld, ptr(a.X), n, a.ld, ptr(out), ld, dev.stream), "gpx_se_dgram")
+        dev.launches += 1
+        return out[0, : n * d].cpu().numpy().reshape(n, d)
 
 
 class KernelMehlerND(Kernel):

@@ -211,6 +211,27 @@ int gpx_set_mask(gpx_handle h, uint8_t* mask, const int64_t* idx_dev, uint8_t va
 int gpx_store_pivot(gpx_handle h, const double* rec, int64_t n, double* U, int64_t ldu, int64_t* picks,
                     double* scores, void* stream);
 
+/* ---- callers of the hot path (continuous optimisers, model fitting) --------------------------- */
+
+/* Kernel derivative Gram, squared-exponential only (kernels.py:146-181, KernelSquaredExponential.derivative):
+ *     out[i*ld + j*d + k] = -signalSize * (Y[j]_k - X[i]_k) / cl_k^2 * k(Y[j], X[i])   (the reference's formula,
+ *     which carries signalSize twice).  ld >= ny*d. */
+int gpx_se_dgram(gpx_handle h, const double* X, int64_t nx, int64_t ldx, const double* Y, int64_t ny, int64_t ldy,
+                 double* out, int64_t ld, void* stream);
+
+/* Posterior-variance gradient with respect to the design coordinates (GP.evaluateVarianceDerivative, gp.py:282-341):
+ *     out[(j*d+k)*ldx + m] = 2 At[j,m] ( D(x_m, p_j)[k] - Qneg[(j*d+k), m] ),   At = P K(D, X) (n x ldx),
+ *     Qneg = -(dK/dp)^T At from gpx_se_dgram + gpx_dgemm_tn_sub.  P: design points, X: query points. */
+int gpx_se_var_grad(gpx_handle h, const double* P, int64_t n, int64_t ldp, const double* X, int64_t M, int64_t ldx,
+                    const double* At, const double* Qneg, double* out, void* stream);
+
+/* out[r] = scale * sum_c A[r,c], fixed order (row mean of the gradient matrix = costFunctionGP_IVAR.derivative,
+ * experimentalDesign.py:166-169). */
+int gpx_rowsum(gpx_handle h, const double* A, int64_t rows, int64_t cols, int64_t ld, double scale, double* out, void* stream);
+
+/* out[0] = log det(U^T U) = 2 sum log U_ii  (np.linalg.slogdet at gp.py:432 for the marginal log-likelihood). */
+int gpx_logdet_chol(gpx_handle h, const double* U, int64_t n, int64_t ld, double* out, void* stream);
+
 /* Yard-stick kernels used only by bench.py to establish the FP64 ceilings on the box. */
 int gpx_bench_dmma(gpx_handle h, int64_t iters, double* sink, void* stream);
 int gpx_bench_dfma(gpx_handle h, int64_t iters, double* sink, void* stream);

@@ -443,3 +443,53 @@ def fast_design_state(kern, design, x, noise):
     low = np.linalg.cholesky(kern.gram(design, design) + noise * np.eye(n))
     w = solve_triangular(low, kern.gram(design, x), lower=True)
     return w, kern.prior(x) - np.sum(w * w, axis=0)
+
+
+# --------------------------------------------------------------------------
+# SURVEY.md 8(f) widening: marginal log-likelihood and the IVAR gradient (squared-exponential kernels)
+# --------------------------------------------------------------------------
+def ref_loglike(kern, pts, evals, noise):
+    """gp.py:394-446 -- pinv + slogdet marginal log-likelihood."""
+    cov = ref_covariance_matrix(kern, pts, noise)
+    inv = np.linalg.pinv(cov)
+    _, logdet = np.linalg.slogdet(cov)
+    return -0.5 * np.dot(evals, np.dot(inv, evals)) - 0.5 * logdet - len(evals) / 2.0 * np.log(2.0 * np.pi)
+
+
+def fast_loglike(kern, pts, evals, noise):
+    """Cholesky restatement: -1/2 |L^-1 y|^2 - sum log L_ii - n/2 log 2 pi."""
+    from scipy.linalg import solve_triangular
+    low = np.linalg.cholesky(kern.gram(pts, pts) + noise * np.eye(len(pts)))
+    z = solve_triangular(low, evals, lower=True)
+    return -0.5 * float(z @ z) - float(np.sum(np.log(np.diag(low)))) - len(evals) / 2.0 * np.log(2.0 * np.pi)
+
+
+def se_derivative(kern, x1, x2):
+    """kernels.py:146-181 -- out[j,i] = 'dK(x1[j], x2)/dx1[j,i]' AS THE REFERENCE COMPUTES IT:
+    -signalSize * (x1 - x2)/cl^2 * evaluate(x1, x2).  evaluate already carries signalSize, so the result is
+    signalSize times the true derivative; parity means reproducing that."""
+    assert kern.family == SE and x2.shape[0] == 1
+    r = kern.evaluate(x1, x2)
+    return -kern.signal * (x1 - x2) / kern.cl ** 2.0 * r[:, None]
+
+
+def fast_variance_derivative(kern, design, newpt, noise):
+    """gp.py:282-341 (noiseFunc None) restated without the n*d python loop:
+        a = K(newpt, D) P ;  T_j[m,k] = -derivative(newpt, p_j)[m,k] ;  dc_(j,k)[c] = derivative(D, p_j)... see below
+        out[j*d+k, m] = -2 a[m,j] T_j[m,k] + 2 a[m,j] sum_c dc_(j,k)[c] a[m,c]
+    Returns the (n*d, M) matrix; the IVAR gradient (experimentalDesign.py:166-169) is its row mean."""
+    n, d = design.shape
+    m = newpt.shape[0]
+    kdd = kern.gram(design, design) + noise * np.eye(n)
+    a = np.linalg.solve(kdd, kern.gram(design, newpt)).T  # (M, n) = totEvals . precision
+    out = np.zeros((n * d, m))
+    for j in range(n):
+        p = design[j:j + 1]
+        t_j = -se_derivative(kern, newpt, p)              # derivTotal[j]            gp.py:316
+        # derivCovTotal[:, j, k] (gp.py:314,329-330): d K(p_j, p_c) / d p_j,k for every c, as the reference's
+        # derivative() computes it = -(derivative of K(p_c, p_j) with respect to p_c)
+        dc = -se_derivative(kern, design, p)
+        for k in range(d):
+            q = a @ dc[:, k]                              # sum_c dc[c] a[m,c]
+            out[j * d + k] = -2.0 * a[:, j] * t_j[:, k] + 2.0 * a[:, j] * q
+    return out

@@ -235,13 +235,48 @@ def gen_greedy_mi(out):
 
 
 def main():
+    only = sys.argv[1:]
     for fname, gen in [("kernels.npz", gen_kernels), ("gram.npz", gen_gram), ("gp.npz", gen_gp),
                        ("greedy_var.npz", gen_greedy_var), ("greedy_ivar.npz", gen_greedy_ivar),
-                       ("greedy_mi.npz", gen_greedy_mi)]:
+                       ("greedy_mi.npz", gen_greedy_mi), ("next.npz", gen_next)]:
+        if only and fname not in only:
+            continue
         out = {}
         gen(out)
         np.savez_compressed(os.path.join(HERE, fname), **out)
         print(fname, len(out), "arrays", os.path.getsize(os.path.join(HERE, fname)) // 1024, "KiB")
+
+
+
+def gen_next(out):
+    """SURVEY.md 8(f) widening: marginal log-likelihood (gp.py:373-446) and the IVAR gradient with respect to the
+    design coordinates (experimentalDesign.py:148-179 -> gp.py:282-341 -> kernels.py:146-181)."""
+    rng = np.random.default_rng(107)
+    for name, noise in [("se_ard_2d_wide", 1e-6), ("matern_5d", 1e-4), ("mehler_3d", 1e-2), ("se_ard_10d", 1e-6)]:
+        kern, d = mk_kernel(name)
+        nodes = sample(rng, name, 35, d)
+        fvals = np.cos(nodes.sum(axis=1))
+        gp = rgp.GP(kern, noise)
+        out[f"next/loglike/{name}/nodes"] = nodes
+        out[f"next/loglike/{name}/fvals"] = fvals
+        out[f"next/loglike/{name}/noise"] = np.float64(noise)
+        out[f"next/loglike/{name}/value"] = np.float64(gp.computeLogLike(nodes, fvals))
+    for name, noise, n, m in [("se_ard_2d_wide", 1e-6, 9, 400), ("se_ard_10d", 1e-6, 14, 300), ("se_iso_1d", 1e-4, 6, 200)]:
+        kern, d = mk_kernel(name)
+        design = sample(rng, name, n, d)
+        mc = sample(rng, name, m, d)
+        one = sample(rng, name, 1, d)
+        gp = rgp.GP(kern, noise)
+        gp.addNodesAndComputeCovariance(design)
+        cf = red.costFunctionGP_IVAR(gp, n, Space(d, None, None, noise=None), mcPoints=mc)
+        out[f"next/grad/{name}/design"] = design
+        out[f"next/grad/{name}/mc"] = mc
+        out[f"next/grad/{name}/one"] = one
+        out[f"next/grad/{name}/noise"] = np.float64(noise)
+        out[f"next/grad/{name}/kderiv"] = kern.derivative(mc, one)
+        out[f"next/grad/{name}/var_deriv"] = gp.evaluateVarianceDerivative(mc[:64])
+        out[f"next/grad/{name}/ivar_deriv"] = cf.derivative(design)
+        out[f"next/grad/{name}/cond"] = np.float64(np.linalg.cond(gp.covarianceMatrix))
 
 
 if __name__ == "__main__":

@@ -594,3 +594,60 @@ def test_score_ivar_unpadded_operands_use_the_generic_core(gx):
     got = score[:Cn].cpu().numpy()
     assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-9
     assert int(idx.item()) == int(np.argmin(ref)) and best.item() == got.min()
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY.md 8(f) widening: marginal log-likelihood and the IVAR gradient, golden vectors of the reference
+# ------------------------------------------------------------------------------------------------
+def test_next_loglike_golden(gx, golden):
+    z = golden("next")
+    for name in sorted({k.split("/")[2] for k in z.files if k.startswith("next/loglike/")}):
+        k = product_kernel(name)
+        nodes, fvals, noise = z[f"next/loglike/{name}/nodes"], z[f"next/loglike/{name}/fvals"], float(z[f"next/loglike/{name}/noise"])
+        ref = float(z[f"next/loglike/{name}/value"])
+        got = gx.gp.GP(k, noise).computeLogLike(nodes, fvals)
+        # pinv/slogdet vs Cholesky: cond * eps on the quadratic form (fast_loglike meets the same bound on the CPU)
+        assert abs(got - ref) <= 1e-7 * abs(ref), (name, got, ref)
+        assert abs(got - orc.fast_loglike(spec(name), nodes, fvals, noise)) <= 1e-10 * abs(ref)
+
+
+def test_next_ivar_gradient_golden(gx, golden):
+    z = golden("next")
+    for name in sorted({k.split("/")[2] for k in z.files if k.startswith("next/grad/")}):
+        k = product_kernel(name)
+        design, mc, one = z[f"next/grad/{name}/design"], z[f"next/grad/{name}/mc"], z[f"next/grad/{name}/one"]
+        noise, cond = float(z[f"next/grad/{name}/noise"]), float(z[f"next/grad/{name}/cond"])
+        tol = max(1e-9, 100 * cond * EPS)
+        np.testing.assert_allclose(k.derivative(mc, one), z[f"next/grad/{name}/kderiv"], rtol=RTOL_K, atol=1e-300)
+        g = gx.gp.GP(k, noise)
+        g.addNodesAndComputeCovariance(design)
+        ref = z[f"next/grad/{name}/var_deriv"]
+        got = g.evaluateVarianceDerivative(mc[:64])
+        assert got.shape == ref.shape
+        assert np.max(np.abs(got - ref)) <= tol * np.max(np.abs(ref)), name
+        cf = gx.ed.costFunctionGP_IVAR(g, design.shape[0], gx.Space(k.dimension, None, None), mcPoints=mc)
+        gref = z[f"next/grad/{name}/ivar_deriv"]
+        ggot = cf.derivative(design)
+        assert ggot.shape == gref.shape and np.max(np.abs(ggot - gref)) <= tol * np.max(np.abs(gref)), name
+    with pytest.raises(AttributeError):
+        gm = gx.gp.GP(product_kernel("matern_5d"), 1e-4)
+        gm.addNodesAndComputeCovariance(np.zeros((3, 5)) + np.arange(3)[:, None])
+        gm.evaluateVarianceDerivative(np.zeros((4, 5)))
+
+
+def test_ivar_gradient_matches_finite_differences(gx):
+    """Property check independent of the reference: with signalSize = 1 the gradient is the true derivative of
+    costFunctionGP_IVAR.evaluate with respect to the design coordinates."""
+    from gpexp_b200 import kernels as K
+    rng = np.random.default_rng(8)
+    k = K.KernelSquaredExponential([0.4, 0.6, 0.5], 1.0, 3)
+    design, mc = rng.uniform(-1, 1, (7, 3)), rng.uniform(-1, 1, (5000, 3))
+    cf = gx.ed.costFunctionGP_IVAR(gx.gp.GP(k, 1e-6), 7, gx.Space(3, None, None), mcPoints=mc)
+    g = cf.derivative(design).reshape(7, 3)
+    h = 1e-6
+    for (j, q) in [(0, 0), (3, 2), (6, 1)]:
+        dp, dm = design.copy(), design.copy()
+        dp[j, q] += h
+        dm[j, q] -= h
+        fd = (cf.evaluate(dp) - cf.evaluate(dm)) / (2 * h)
+        assert abs(fd - g[j, q]) <= 1e-5 * max(abs(fd), 1e-3), (j, q, fd, g[j, q])

@@ -124,3 +124,27 @@ def test_greedy_mi(golden):
     for j in (0, 7, 33):
         got = orc.ref_mi_cost(k, pool, noise, j, [int(z["gmi/1/start"])])[0]
         assert abs(got - z["gmi/1/scores"][1][j]) <= 1e-12 * abs(got)
+
+
+def test_next_loglike_and_ivar_gradient(golden):
+    z = golden("next")
+    for name in keys(z, "next"):
+        pass
+    for name in sorted({k.split("/")[2] for k in z.files if k.startswith("next/loglike/")}):
+        k = spec(name)
+        nodes, fvals, noise = z[f"next/loglike/{name}/nodes"], z[f"next/loglike/{name}/fvals"], float(z[f"next/loglike/{name}/noise"])
+        ref = float(z[f"next/loglike/{name}/value"])
+        assert abs(orc.ref_loglike(k, nodes, fvals, noise) - ref) <= 1e-9 * abs(ref)
+        assert abs(orc.fast_loglike(k, nodes, fvals, noise) - ref) <= 1e-7 * abs(ref), name
+    for name in sorted({k.split("/")[2] for k in z.files if k.startswith("next/grad/")}):
+        k = spec(name)
+        design, mc, one = z[f"next/grad/{name}/design"], z[f"next/grad/{name}/mc"], z[f"next/grad/{name}/one"]
+        noise = float(z[f"next/grad/{name}/noise"])
+        np.testing.assert_allclose(orc.se_derivative(k, mc, one), z[f"next/grad/{name}/kderiv"], rtol=1e-13, atol=1e-300)
+        full = orc.fast_variance_derivative(k, design, mc, noise)
+        ref = z[f"next/grad/{name}/var_deriv"]
+        cond = float(z[f"next/grad/{name}/cond"])
+        tol = max(1e-9, 100 * cond * 2.2e-16)
+        assert np.max(np.abs(full[:, :64] - ref)) <= tol * np.max(np.abs(ref)), name
+        g = z[f"next/grad/{name}/ivar_deriv"]
+        assert np.max(np.abs(full.mean(axis=1) - g)) <= tol * np.max(np.abs(g)), name
