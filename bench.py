@@ -348,7 +348,16 @@ def run_ours(args):
                                                        ptr(eng.Wc), cand.ld, n, ptr(eng.varC), dev.stream)))
         eng.restore(snap2)
         app_gbs = 8.0 * (n + 2) * cand.n / (t_app * 1e-3) / 1e9
-        extras = {"gram_gbs": gram_gbs, "gram_frac_of_measured_hbm": gram_gbs / hbm, "gram_block": [nx, cand.n],
+        # 8(f) widening: the analytic IVAR gradient the SLSQP polish calls (experimentalDesign.py:148-179)
+        t0 = time.perf_counter()
+        grad = cf.derivative(des_p)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        grad = cf.derivative(des_p)
+        torch.cuda.synchronize()
+        grad_ms = (time.perf_counter() - t0) * 1e3
+        extras = {"ivar_gradient_ms": grad_ms, "ivar_gradient_shape": [int(grad.size)],
+                  "gram_gbs": gram_gbs, "gram_frac_of_measured_hbm": gram_gbs / hbm, "gram_block": [nx, cand.n],
                   "gram_note": "algorithmic 8 B written per element; the kernel is FP64-issue bound by exp(), see DESIGN.md",
                   "append_row_gbs": app_gbs, "append_row_frac_of_measured_hbm": app_gbs / hbm, "hbm_peak_gbs": hbm}
         del G

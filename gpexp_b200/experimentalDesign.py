@@ -150,6 +150,91 @@ class costFunctionGP_MI(costFunctionBase):
         return eng.scores[int(index): int(index) + 1].cpu().numpy()
 
 
+class ExperimentalDesign(object):
+    """Base of the continuous optimisers (experimentalDesign.py:296-343): holds the cost function and the
+    probability-density bound penalty."""
+    nMCpoints = 10000
+
+    def __init__(self, costFunction, nPoints, nDims, **kwargs):
+        self.costFunction = costFunction
+        self.nPoints = nPoints
+        self.nDims = nDims
+        super(ExperimentalDesign, self).__init__()
+
+    def boundsFunction(self, optPoints):
+        """+1 if every point has non-zero density under space.probDensity, else -1 (:310-343)."""
+        if len(np.shape(optPoints)) == 1:
+            optPoints = np.reshape(optPoints, (int(len(optPoints) / self.nDims), self.nDims))
+        out = self.costFunction.space.probDensity(optPoints)
+        out[out == 0.0] = -1e0
+        if np.min(out) < 0.0:
+            return -1e0
+        else:
+            return 1e0
+
+
+class ExperimentalDesignDerivative(ExperimentalDesign):
+    """SLSQP polish of a design with the analytic IVAR gradient (experimentalDesign.py:345-497).  The objective and
+    its gradient are the device cost function (`evaluate`, `derivative`); the optimiser itself is scipy's SLSQP, the
+    branch the reference takes when nlopt is not installed (:461-497)."""
+
+    def __init__(self, costFunction, nPoints, nDims):
+        self.addObj = lambda x: 0
+        self.addGrad = lambda x: 0
+        super(ExperimentalDesignDerivative, self).__init__(costFunction, nPoints, nDims)
+
+    def addPenaltyToObjective(self, addObj, addGrad):
+        self.addObj = addObj
+        self.addGrad = addGrad
+
+    def beginWithVarGreedy(self, nodesKeep=None, lbounds=[], rbounds=[]):
+        """Start from the greedy max-variance ("entropy") design over the MC points, then polish (:379-404)."""
+        kTemp = copy.copy(self.costFunction.gaussianProcess.kernel)
+        if nodesKeep is not None:
+            mcPoints = np.concatenate((nodesKeep, self.costFunction.mcPoints), axis=0)
+            indKeep = np.arange(len(nodesKeep)).tolist()
+        else:
+            try:
+                mcPoints = self.costFunction.mcPoints[:]
+            except AttributeError:
+                nMC = 1000
+                mcPoints = self.costFunction.space.sample((nMC, self.costFunction.space.dimension))
+            indKeep = []
+        startVals = performGreedyVarExperimentalDesign(kTemp, mcPoints, self.nPoints, self.nDims, indKeepStart=indKeep)
+        endVals = self.begin([startVals], lbounds, rbounds)
+        return endVals
+
+    def begin(self, startValues, lbounds=[], rbounds=[]):
+        """Minimise the cost from every start value and return the best end design (:406-497, scipy branch)."""
+        from scipy.optimize import fmin_slsqp as slsqp
+
+        def func(xIn, *args):
+            in0 = np.reshape(xIn, (int(len(xIn) / self.nDims), self.nDims))
+            out = self.costFunction.evaluate(in0) - 10.0 * np.min(np.array([self.boundsFunction(in0), 0.0]))
+            return out
+
+        def grad(xIn, *args):
+            in0 = np.reshape(xIn, (int(len(xIn) / self.nDims), self.nDims))
+            return self.costFunction.derivative(in0)
+
+        if len(lbounds) == 0:
+            lb = -100.0 * np.ones((len(startValues[0]) * self.nDims))
+            ub = 100.0 * np.ones((len(startValues[0]) * self.nDims))
+            bounds = list(zip(lb, ub))
+        else:
+            bounds = list(zip(lbounds, rbounds))
+        sol = []
+        obj = np.zeros((len(startValues)))
+        for ii in range(len(startValues)):
+            pts = slsqp(func, startValues[ii].reshape((len(startValues[ii]) * self.nDims)), fprime=grad, bounds=bounds,
+                        acc=1e-6, iprint=1 if VERBOSE else 0)
+            sol.append(pts)
+            obj[ii] = func(pts)
+        indBest = np.argmin(obj)
+        endVals = np.reshape(sol[indBest], (int(len(sol[indBest]) / self.nDims), self.nDims))
+        return endVals
+
+
 def performGreedyMIExperimentalDesign(costFuncMI, nPoints, start=0, shard=None):
     """Greedy MI design over the cost function's pool (experimentalDesign.py:753-785).
     Returns the chosen POINTS (as the reference does); the indices are left in

@@ -277,6 +277,24 @@ def gen_next(out):
         out[f"next/grad/{name}/var_deriv"] = gp.evaluateVarianceDerivative(mc[:64])
         out[f"next/grad/{name}/ivar_deriv"] = cf.derivative(design)
         out[f"next/grad/{name}/cond"] = np.float64(np.linalg.cond(gp.covarianceMatrix))
+    # continuous polish of a design with SLSQP (ExperimentalDesignDerivative.begin, experimentalDesign.py:406-497;
+    # nlopt is absent, so the scipy branch runs), started from the greedy max-variance design (:379-404)
+    kern, d = mk_kernel("se_ard_2d_wide")
+    mc = sample(rng, "se", 600, d)
+    dens = lambda p: np.all(np.abs(p) <= 1.0, axis=1).astype(float)  # noqa: E731
+    space = Space(d, lambda s: rng.uniform(-1, 1, s), dens, noise=None)
+    gp = rgp.GP(kern, 1e-6)
+    cf = red.costFunctionGP_IVAR(gp, 5, space, mcPoints=mc)
+    exp = red.ExperimentalDesignDerivative(cf, 5, d)
+    start = quiet(red.performGreedyVarExperimentalDesign, kern, mc, 5, d)
+    end = quiet(exp.begin, [start], list(-np.ones(10)), list(np.ones(10)))
+    end2 = quiet(exp.beginWithVarGreedy, None, list(-np.ones(10)), list(np.ones(10)))
+    out["next/slsqp/mc"] = mc
+    out["next/slsqp/start"] = start
+    out["next/slsqp/end"] = end
+    out["next/slsqp/end_greedy"] = end2
+    out["next/slsqp/cost_start"] = np.float64(cf.evaluate(start))
+    out["next/slsqp/cost_end"] = np.float64(cf.evaluate(end))
 
 
 if __name__ == "__main__":

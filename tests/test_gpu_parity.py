@@ -651,3 +651,24 @@ def test_ivar_gradient_matches_finite_differences(gx):
         dm[j, q] -= h
         fd = (cf.evaluate(dp) - cf.evaluate(dm)) / (2 * h)
         assert abs(fd - g[j, q]) <= 1e-5 * max(abs(fd), 1e-3), (j, q, fd, g[j, q])
+
+
+def test_next_slsqp_polish_golden(gx, golden):
+    """ExperimentalDesignDerivative.begin / beginWithVarGreedy (experimentalDesign.py:379-497): same start design, and
+    the SLSQP polish driven by the device cost + gradient lands on the reference's end design."""
+    z = golden("next")
+    mc = z["next/slsqp/mc"]
+    k = product_kernel("se_ard_2d_wide")
+    dens = lambda p: np.all(np.abs(p) <= 1.0, axis=1).astype(float)  # noqa: E731
+    space = gx.Space(2, None, dens, noise=None)
+    cf = gx.ed.costFunctionGP_IVAR(gx.gp.GP(k, 1e-6), 5, space, mcPoints=mc)
+    exp = gx.ed.ExperimentalDesignDerivative(cf, 5, 2)
+    start = gx.ed.performGreedyVarExperimentalDesign(k, mc, 5, 2)
+    assert np.array_equal(start, z["next/slsqp/start"])
+    assert abs(cf.evaluate(start) - float(z["next/slsqp/cost_start"])) <= 1e-9 * float(z["next/slsqp/cost_start"])
+    end = exp.begin([start], list(-np.ones(10)), list(np.ones(10)))
+    # SLSQP stops at acc = 1e-6 on the objective: compare the optimum, and the design to the optimiser's own accuracy
+    assert abs(cf.evaluate(end) - float(z["next/slsqp/cost_end"])) <= 1e-6
+    assert np.max(np.abs(end - z["next/slsqp/end"])) <= 5e-3
+    end2 = exp.beginWithVarGreedy(None, list(-np.ones(10)), list(np.ones(10)))
+    assert np.max(np.abs(end2 - end)) <= 1e-9
