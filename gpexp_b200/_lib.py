@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libgpexp_b200.so")
+LIB_PATH = os.environ.get("GPX_LIB") or os.path.join(HERE, "lib", "libgpexp_b200.so")  # GPX_LIB: A/B builds only
 
 GPX_MAX_DIM = 16
 GPX_KROWS = 16

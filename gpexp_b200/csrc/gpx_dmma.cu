@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(WM * 64, WM == 4 ? 1 : 2)
 // ---------------------------------------------------------------------------------------------
 // TMA + mbarrier IVAR contraction (the hot kernel): operand chunks arrive by TMA bulk copies
 // (cp.async.bulk -> UBLKCP) that complete on mbarriers; the eight warps do LDS.128 + DMMA and take turns
-// (warp g mod 8 for chunk g+3) at issuing the 33 bulk copies of a chunk -- a ninth, dedicated producer warp
+// (warp g mod 8 for chunk g+WS_AHEAD) at issuing the bulk copies of a chunk -- a ninth, dedicated producer warp
 // would put three warps on one sub-partition and cap everybody at 168 registers.  No CTA-wide barrier in
 // the main loop, so warps drift apart and one warp's exp prologue / epilogue overlaps the other warp's
 // DMMA stream on the same sub-partition.
@@ -397,9 +397,19 @@ constexpr int WS_CONSUMERS = 8;
 constexpr int WS_THREADS = WS_CONSUMERS * 32;
 constexpr int WS_BM = 128;
 constexpr int WS_LD = 132;
-constexpr int WS_STAGE = BK * 2 * WS_LD;  // doubles
-constexpr int WS_STAGES = 6;               // ring depth
-constexpr int WS_AHEAD = 3;                // chunks in flight; the refilled stage was released 3 chunks ago
+// Ring geometry.  Measured on B200 (n = 2047 / n = 255, C = M = 100k): 16 rows x 6 stages, 3 chunks ahead: 34.18 TFLOP/s /
+// 165.5 ms; 32 rows x 3 stages, 1 ahead: 34.70 / 165.3 ms; 32 x 3 stages, 2 ahead: 23.7 / 240 ms -- the stage that is
+// refilled must have been released at least one whole chunk ago, or the producing warp blocks on the slowest consumer.
+#ifndef GPX_WS_BK
+#define GPX_WS_BK 32
+#define GPX_WS_STAGES 3
+#define GPX_WS_AHEAD 1
+#endif
+constexpr int WS_BK = GPX_WS_BK;           // K rows per chunk
+constexpr int WS_KSTEPS = WS_BK / 4;
+constexpr int WS_STAGE = WS_BK * 2 * WS_LD;  // doubles
+constexpr int WS_STAGES = GPX_WS_STAGES;   // ring depth
+constexpr int WS_AHEAD = GPX_WS_AHEAD;     // chunks in flight ahead of the consumers
 constexpr int WS_SMEM_DOUBLES = WS_STAGES * WS_STAGE + WS_STAGES * WS_BM + BN + 4 * BN + 2 * WS_STAGES + 256;
 constexpr size_t WS_SMEM_BYTES = (size_t)WS_SMEM_DOUBLES * sizeof(double);
 
@@ -452,7 +462,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
     int64_t it_end = it_begin + a.tiles_per_cta;
     if (it_end > itiles) it_end = itiles;
     const int ntiles = it_end > it_begin ? (int)(it_end - it_begin) : 0;
-    const int kch = (a.K + BK - 1) / BK;
+    const int kch = (a.K + WS_BK - 1) / WS_BK;
     const int T = 1 + kch;
     const int G = ntiles * T;
 
@@ -490,14 +500,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
             ksteps = a.dpad >> 2;
         } else {
             const int kc = pch - 1;
-            srcA = a.A + (int64_t)kc * BK * a.lda + i0;
-            srcB = a.B + (int64_t)kc * BK * a.ldb + j0;
-            const int rem = a.K - kc * BK;
-            krows = rem < BK ? rem : BK;
-            ksteps = rem >= BK ? 4 : ((rem + 3) >> 2);
+            srcA = a.A + (int64_t)kc * WS_BK * a.lda + i0;
+            srcB = a.B + (int64_t)kc * WS_BK * a.ldb + j0;
+            const int rem = a.K - kc * WS_BK;
+            krows = rem < WS_BK ? rem : WS_BK;
+            ksteps = rem >= WS_BK ? WS_KSTEPS : ((rem + 3) >> 2);
         }
         double* stA = smem + s * WS_STAGE;
-        double* stB = stA + BK * LD;
+        double* stB = stA + WS_BK * LD;
         if (krows < ksteps * 4) {
             // K tail: rows the DMMAs will read but the operand does not have -> explicit zeros (lane -> column pair)
             for (int r = krows; r < ksteps * 4; ++r) {
@@ -528,7 +538,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         double acc[4][8][2];
         double af0[4], bf0[8];
         const int fa = q4 * LD + wm * 32 + g4 * 2;
-        const int fb = BK * LD + q4 * LD + wn * 64 + g4 * 2;
+        const int fb = WS_BK * LD + q4 * LD + wn * 64 + g4 * 2;
         int tl = 0, ch = 0;
         for (int g = 0; g < G; ++g) {
             const int s = g % WS_STAGES;
@@ -548,8 +558,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
             if (ch == 0) {
                 ksteps = a.dpad >> 2;
             } else {
-                const int rem = a.K - (ch - 1) * BK;
-                ksteps = rem >= BK ? 4 : ((rem + 3) >> 2);
+                const int rem = a.K - (ch - 1) * WS_BK;
+                ksteps = rem >= WS_BK ? WS_KSTEPS : ((rem + 3) >> 2);
             }
             // single-buffered fragments: the other warp of the sub-partition covers the LDS latency (double
             // buffering measured identical: 34.44 vs 34.43 TFLOP/s at n = 4095)
