@@ -356,7 +356,18 @@ def run_ours(args):
         grad = cf.derivative(des_p)
         torch.cuda.synchronize()
         grad_ms = (time.perf_counter() - t0) * 1e3
-        extras = {"ivar_gradient_ms": grad_ms, "ivar_gradient_shape": [int(grad.size)],
+        # a7: posterior variance of 100k points given the 255-point design, from host arrays (GP.evaluateVariance)
+        g_pv = gpmod.GP(kern, CFG["noise"])
+        g_pv.addNodesAndComputeCovariance(des_p)
+        g_pv.evaluateVariance(mc_p)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pv = g_pv.evaluateVariance(mc_p)
+        torch.cuda.synchronize()
+        pv_ms = (time.perf_counter() - t0) * 1e3
+        extras = {"posterior_variance_ms": pv_ms, "posterior_variance_points_per_s": mc_p.shape[0] / pv_ms * 1e3,
+                  "posterior_variance_min": float(pv.min()),
+                  "ivar_gradient_ms": grad_ms, "ivar_gradient_shape": [int(grad.size)],
                   "gram_gbs": gram_gbs, "gram_frac_of_measured_hbm": gram_gbs / hbm, "gram_block": [nx, cand.n],
                   "gram_note": "algorithmic 8 B written per element; the kernel is FP64-issue bound by exp(), see DESIGN.md",
                   "append_row_gbs": app_gbs, "append_row_frac_of_measured_hbm": app_gbs / hbm, "hbm_peak_gbs": hbm}

@@ -24,6 +24,9 @@
 #ifndef GPX_DEFAULT_WM
 #define GPX_DEFAULT_WM 2
 #endif
+#ifndef GPX_DEFAULT_IVAR_TN
+#define GPX_DEFAULT_IVAR_TN 8
+#endif
 
 namespace {
 
@@ -393,8 +396,6 @@ __global__ void __launch_bounds__(WM * 64, WM == 4 ? 1 : 2)
 // DMMA stream on the same sub-partition.
 // Requires fully padded operands: lda, ldb multiples of 128 covering whole tiles (the engines guarantee it).
 // ---------------------------------------------------------------------------------------------
-constexpr int WS_CONSUMERS = 8;
-constexpr int WS_THREADS = WS_CONSUMERS * 32;
 constexpr int WS_BM = 128;
 constexpr int WS_LD = 132;
 // Ring geometry.  Measured on B200 (n = 2047 / n = 255, C = M = 100k): 16 rows x 6 stages, 3 chunks ahead: 34.18 TFLOP/s /
@@ -442,10 +443,35 @@ __device__ __forceinline__ void bulk_g2s(double* dst, const double* src, unsigne
                  : "memory");
 }
 
-template <int FAM>
-__global__ void __launch_bounds__(WS_THREADS, 1)
+// TN = B fragments per warp: 8 -> 8 warps of 32x64 (254 registers), 4 -> 16 warps of 32x32 (<= 128 registers, four
+// warps per sub-partition: the DMMA pipe only idles when all four are outside their DMMA stream at once).
+template <int TN>
+struct WsCfg {
+    static constexpr int WN = BN / (TN * 8);      // warps along the candidate dimension
+    static constexpr int NW = 4 * WN;             // warps per CTA
+    static constexpr int NT = NW * 32;
+};
+
+template <int TN>
+__device__ __forceinline__ void load_frags_ws(double (&af)[4], double (&bf)[TN], const double* pa, const double* pb, int ks) {
+#pragma unroll
+    for (int t2 = 0; t2 < 2; ++t2) {
+        const double2 v = *reinterpret_cast<const double2*>(pa + ks * 4 * WS_LD + t2 * 16);
+        af[t2 * 2] = v.x;
+        af[t2 * 2 + 1] = v.y;
+    }
+#pragma unroll
+    for (int u2 = 0; u2 < TN / 2; ++u2) {
+        const double2 v = *reinterpret_cast<const double2*>(pb + ks * 4 * WS_LD + u2 * 16);
+        bf[u2 * 2] = v.x;
+        bf[u2 * 2 + 1] = v.y;
+    }
+}
+
+template <int FAM, int TN>
+__global__ void __launch_bounds__(WsCfg<TN>::NT, 1)
     ivar_ws_kernel(const __grid_constant__ CoreArgs a, const __grid_constant__ KParams kp) {
-    constexpr int BM = WS_BM, LD = WS_LD;
+    constexpr int BM = WS_BM, LD = WS_LD, NW = WsCfg<TN>::NW, NT = WsCfg<TN>::NT, WCOLS = TN * 8;
     extern __shared__ __align__(16) double smem[];
     double* s_alpha = smem + WS_STAGES * WS_STAGE;  // [WS_STAGES][BM], travels with the prologue chunk
     double* s_beta = s_alpha + WS_STAGES * BM;
@@ -470,19 +496,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 #pragma unroll
         for (int s = 0; s < WS_STAGES; ++s) {
             mbar_init(full + s, 1);
-            mbar_init(empty + s, WS_CONSUMERS);
+            mbar_init(empty + s, NW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (tid < BN) s_beta[tid] = (j0 + tid < a.J) ? a.Bs[j0 + tid] : 0.0;
-    s_tab[tid] = kp.signal * gpx_exp2_tab[tid];
+    if (tid < 256) s_tab[tid] = kp.signal * gpx_exp2_tab[tid];
     __syncthreads();
 
     double rs[2] = {0.0, 0.0};
-    const int wm = warp & 3, wn = (warp >> 2) & 1;
+    const int wm = warp & 3, wn = warp >> 2;
     const int g4 = lane >> 2, q4 = lane & 3;
 
-    // ---- producer step, executed by one warp per chunk; all addresses are warp-uniform so that the 33 bulk
+    // ---- producer step, executed by one warp per chunk; all addresses are warp-uniform so that the bulk
     //      copies issue back to back from one lane (UBLKCP takes uniform registers) -----------------------
     auto produce = [&](int c) {
         if (c >= G) return;
@@ -534,22 +560,21 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
     if (warp < WS_AHEAD) produce(warp);
 
     {
-        // ================= consumer warps ===========================================================
-        double acc[4][8][2];
-        double af0[4], bf0[8];
+        double acc[4][TN][2];
+        double af0[4], bf0[TN];
         const int fa = q4 * LD + wm * 32 + g4 * 2;
-        const int fb = WS_BK * LD + q4 * LD + wn * 64 + g4 * 2;
+        const int fb = WS_BK * LD + q4 * LD + wn * WCOLS + g4 * 2;
         int tl = 0, ch = 0;
         for (int g = 0; g < G; ++g) {
             const int s = g % WS_STAGES;
             const unsigned int ph = (unsigned int)(g / WS_STAGES) & 1u;
             const int64_t i0 = (it_begin + tl) * BM;
-            if (warp == (g & (WS_CONSUMERS - 1))) produce(g + WS_AHEAD);
+            if (warp == (g & (NW - 1))) produce(g + WS_AHEAD);
             if (ch == 0) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
+                    for (int u = 0; u < TN; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
             }
             mbar_wait(full + s, ph);
             const double* pa = smem + s * WS_STAGE + fa;
@@ -561,12 +586,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
                 const int rem = a.K - (ch - 1) * WS_BK;
                 ksteps = rem >= WS_BK ? WS_KSTEPS : ((rem + 3) >> 2);
             }
-            // single-buffered fragments: the other warp of the sub-partition covers the LDS latency (double
+            // single-buffered fragments: the other warps of the sub-partition cover the LDS latency (double
             // buffering measured identical: 34.44 vs 34.43 TFLOP/s at n = 4095)
 #pragma unroll 1
             for (int ks = 0; ks < ksteps; ++ks) {
-                load_frags<LD, LD>(af0, bf0, pa, pb, ks);
-                mma_tile(acc, af0, bf0);
+                load_frags_ws<TN>(af0, bf0, pa, pb, ks);
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+#pragma unroll
+                    for (int u = 0; u < TN; ++u) dmma(acc[t][u][0], acc[t][u][1], af0[t], bf0[u]);
             }
             if (ch == 0) {
                 // covariance from the expanded form; accumulators become -k so that the main loop yields T - k
@@ -575,10 +603,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
                 for (int t = 0; t < 4; ++t) {
                     const double al = sal[wm * 32 + (t >> 1) * 16 + g4 * 2 + (t & 1)];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u)
+                    for (int u = 0; u < TN; ++u)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            const double be = s_beta[wn * 64 + (u >> 1) * 16 + (q4 * 2 + e) * 2 + (u & 1)];
+                            const double be = s_beta[wn * WCOLS + (u >> 1) * 16 + (q4 * 2 + e) * 2 + (u & 1)];
                             acc[t][u][e] = -kexpand_tab<FAM>(acc[t][u][e] + al + be, kp, s_tab);
                         }
                 }
@@ -589,44 +617,70 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 
             if (ch == T - 1) {
                 const bool fullt = (i0 + BM <= a.I);
-                double p[8][2];
+                double p[TN][2];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) p[u][0] = p[u][1] = 0.0;
+                for (int u = 0; u < TN; ++u) p[u][0] = p[u][1] = 0.0;
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const int64_t i = i0 + wm * 32 + (t >> 1) * 16 + g4 * 2 + (t & 1);
                     const bool ok = fullt || (i < a.I);
 #pragma unroll
-                    for (int u = 0; u < 8; ++u)
+                    for (int u = 0; u < TN; ++u)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const double v = ok ? acc[t][u][e] : 0.0;
                             p[u][e] = fma(v, v, p[u][e]);
                         }
                 }
+                // butterfly reduce-scatter over the 8 lanes that share q4
                 const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
-                double h[4][2], q[2][2];
+                if (TN == 8) {
+                    // lane g4 ends up owning u = g4 (both e)
+                    double h[4][2], q[2][2];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const double keep = b4 ? p[(u + 4) % TN][e] : p[u][e];
+                            const double send = b4 ? p[u][e] : p[(u + 4) % TN][e];
+                            h[u][e] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                        }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const double keep = b3 ? h[u + 2][e] : h[u][e];
+                            const double send = b3 ? h[u][e] : h[u + 2][e];
+                            q[u][e] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                        }
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const double keep = b4 ? p[u + 4][e] : p[u][e];
-                        const double send = b4 ? p[u][e] : p[u + 4][e];
-                        h[u][e] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                        const double keep = b2 ? q[1][e] : q[0][e];
+                        const double send = b2 ? q[0][e] : q[1][e];
+                        rs[e] += keep + __shfl_xor_sync(0xffffffffu, send, 4);
                     }
+                } else {
+                    // TN == 4: lane g4 ends up owning u = g4 >> 1, e = g4 & 1 (one value)
+                    double h[2][2], q[2];
 #pragma unroll
-                for (int u = 0; u < 2; ++u)
+                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const double keep = b4 ? p[(u + 2) % TN][e] : p[u][e];
+                            const double send = b4 ? p[u][e] : p[(u + 2) % TN][e];
+                            h[u][e] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                        }
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const double keep = b3 ? h[u + 2][e] : h[u][e];
-                        const double send = b3 ? h[u][e] : h[u + 2][e];
-                        q[u][e] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                        const double keep = b3 ? h[1][e] : h[0][e];
+                        const double send = b3 ? h[0][e] : h[1][e];
+                        q[e] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
                     }
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const double keep = b2 ? q[1][e] : q[0][e];
-                    const double send = b2 ? q[0][e] : q[1][e];
-                    rs[e] += keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    {
+                        const double keep = b2 ? q[1] : q[0];
+                        const double send = b2 ? q[0] : q[1];
+                        rs[0] += keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    }
                 }
                 ch = 0;
                 ++tl;
@@ -637,8 +691,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
     }
 
     __syncthreads();
+    if (TN == 8) {
 #pragma unroll
-    for (int e = 0; e < 2; ++e) s_red[wm * BN + wn * 64 + (g4 >> 1) * 16 + (q4 * 2 + e) * 2 + (g4 & 1)] = rs[e];
+        for (int e = 0; e < 2; ++e) s_red[wm * BN + wn * WCOLS + (g4 >> 1) * 16 + (q4 * 2 + e) * 2 + (g4 & 1)] = rs[e];
+    } else {
+        const int u = g4 >> 1, e = g4 & 1;
+        s_red[wm * BN + wn * WCOLS + (u >> 1) * 16 + (q4 * 2 + e) * 2 + (u & 1)] = rs[0];
+    }
     __syncthreads();
     if (tid < BN && j0 + tid < a.J) {
         const double r = ((s_red[tid] + s_red[BN + tid]) + s_red[2 * BN + tid]) + s_red[3 * BN + tid];
@@ -654,19 +713,32 @@ bool ivar_use_tma() {
     }
     return v == 1;
 }
-template <int FAM>
-int launch_ivar_ws(const CoreArgs& a, const KParams& kp, dim3 grid, cudaStream_t st) {
+int ivar_tn() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("GPX_IVAR_TN");
+        v = (e && e[0] == '8') ? 8 : ((e && e[0] == '4') ? 4 : GPX_DEFAULT_IVAR_TN);
+    }
+    return v;
+}
+
+template <int FAM, int TN>
+int launch_ivar_ws_tn(const CoreArgs& a, const KParams& kp, dim3 grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(ivar_ws_kernel<FAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(ivar_ws_kernel<FAM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES);
         if (e != cudaSuccess) {
             gpx_set_error("ivar_ws: cannot opt in to %zu bytes of shared memory: %s", WS_SMEM_BYTES, cudaGetErrorString(e));
             return (int)e;
         }
         configured = true;
     }
-    ivar_ws_kernel<FAM><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(a, kp);
+    ivar_ws_kernel<FAM, TN><<<grid, WsCfg<TN>::NT, WS_SMEM_BYTES, st>>>(a, kp);
     return gpx_check_launch("ivar_ws");
+}
+template <int FAM>
+int launch_ivar_ws(const CoreArgs& a, const KParams& kp, dim3 grid, cudaStream_t st) {
+    return ivar_tn() == 4 ? launch_ivar_ws_tn<FAM, 4>(a, kp, grid, st) : launch_ivar_ws_tn<FAM, 8>(a, kp, grid, st);
 }
 
 // tile shape used by every launch: GPX_WM=2 (64x128, 2 CTAs/SM) or 4 (128x128, 1 CTA/SM)
