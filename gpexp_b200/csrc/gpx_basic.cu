@@ -574,7 +574,6 @@ extern "C" int gpx_transpose(gpx_handle h, const double* in, int64_t rows, int64
     if (rows == 0 || cols == 0) return GPX_OK;
     GPX_REQUIRE(in && out && ld_in >= cols && ld_out >= rows, GPX_EINVAL, "bad arguments");
     const int64_t gy = (rows + 31) / 32;
-    GPX_REQUIRE(gy <= 65535 || true, GPX_ESIZE, "");
     if (gy <= 65535) {
         dim3 grid((unsigned)((cols + 31) / 32), (unsigned)gy);
         transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, rows, cols, ld_in, out, ld_out);

@@ -1,4 +1,4 @@
-// FP64 tensor-core (DMMA.8x8x4) contraction core of the greedy design path.
+// FP64 tensor-core (DMMA.8x8x4) contractions of the greedy design path.
 //
 //   T[i,j] = sum_k A[k*lda + i] * B[k*ldb + j]           both operands K-major (row k contiguous)
 //
@@ -7,12 +7,19 @@
 //
 //   EPI_IVAR   r[j] += sum_i (k(i,j) - T[i,j])^2          K5: IVAR scoring, experimentalDesign.py:105-117 restated
 //   EPI_STORE  out[i,j] = k(i,j) - T[i,j]                  K1+K3: block row of the left-looking TRSM
-//   EPI_SUB    C[i,j]  -= T[i,j]                           K2: Cholesky trailing update / materialised TRSM
+//   EPI_SUB    C[i,j]  -= T[i,j]                           K2: Cholesky trailing update / materialised TRSM / MI set-up
 //
 // sm_100a has no f64 kind in tcgen05, so the FP64 tensor path is warp-level mma.sync.m8n8k4 (SASS DMMA.8x8x4)
-// fed from shared memory.  CTA tile 128x128, 8 warps of 32x64, K chunks of 16 rows through a 4-stage
-// cp.async (LDGSTS) ring, rows padded to 132 doubles so that the 16-byte fragment loads are conflict-free.
-// The fragment <-> matrix index map is permuted so that every thread reads 2 adjacent doubles per LDS.128:
+// fed from shared memory.  Two kernels share the fragment layout:
+//
+//   ivar_ws_kernel     THE hot kernel (EPI_IVAR on fully padded operands): 128x128 CTA tile, 8 warps of 32x64,
+//                      operand chunks by TMA bulk copies completing on mbarriers (3-stage ring of 32-row chunks),
+//                      no CTA barrier in the main loop, table-driven exp prologue, butterfly column reduction.
+//   dmma_core_kernel   the generic predicated kernel (cp.async ring + __syncthreads, zero-filled edges) used for
+//                      EPI_STORE / EPI_SUB and as the fallback for unpadded IVAR operands.
+//
+// Rows are padded to 132 doubles and the fragment <-> matrix index map is permuted so that every thread reads
+// 2 adjacent doubles per conflict-free LDS.128:
 //   i_local = wm*32 + (t>>1)*16 + (lane>>2)*2 + (t&1)            t = 0..3  (A fragments)
 //   j_local = wn*64 + (u>>1)*16 + (lane>>2)*2 + (u&1)            u = 0..7  (B fragments, load side)
 //   accumulator (t,u,e) sits at column  wn*64 + (u>>1)*16 + ((lane&3)*2+e)*2 + (u&1)

@@ -114,8 +114,5 @@ class Device:
             self.launches += 1
         return PointSet(self, X, n, d)
 
-    def points_from_device(self, X: torch.Tensor, n: int, d: int) -> PointSet:
-        return PointSet(self, X, n, d)
-
     def sync(self) -> None:
         torch.cuda.current_stream(self.torch_device).synchronize()
