@@ -736,3 +736,90 @@ extern "C" int gpx_local_index(gpx_handle h, const double* rec, int64_t offset, 
     local_index_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(rec, offset, count, out2);
     return gpx_check_launch("gpx_local_index");
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Resident posterior covariance (the O(M*C) bytes/step alternative to the per-step contraction):
+//     cov[m,c] = k(m,c) - sum_{i<n} W_M[i,m] W_C[i,c]   is kept in HBM (8*M*C bytes) and every greedy step applies
+//     cov -= a b^T   (a = the new row of W_M, b = the new row of W_C)  while accumulating  r[c] = sum_m cov[m,c]^2
+// in the same pass: 16 bytes of HBM traffic per (m,c) pair and step, independent of the design size n.
+// Block = 512 columns (16-byte accesses) x one row segment; per-segment partial sums are added in a fixed order.
+// ---------------------------------------------------------------------------------------------
+#define COV_MAX_SEG 32
+
+__global__ void __launch_bounds__(256) cov_update_kernel(double* __restrict__ cov, int64_t ldc, int64_t M, int64_t C,
+                                                          const double* __restrict__ a, const double* __restrict__ b,
+                                                          int64_t rows_per_seg, double* __restrict__ part, int64_t ldp) {
+    const int64_t c = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 2;
+    if (c >= C) return;
+    const int64_t m0 = (int64_t)blockIdx.y * rows_per_seg;
+    int64_t m1 = m0 + rows_per_seg;
+    if (m1 > M) m1 = M;
+    const bool upd = (a != nullptr);
+    double b0 = 0.0, b1 = 0.0;
+    if (upd) {
+        const double2 bb = *reinterpret_cast<const double2*>(b + c);
+        b0 = bb.x;
+        b1 = bb.y;
+    }
+    double r0 = 0.0, r1 = 0.0;
+    double* p = cov + m0 * ldc + c;
+    int64_t m = m0;
+    for (; m + 8 <= m1; m += 8) {
+        double2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcs(reinterpret_cast<const double2*>(p + (int64_t)u * ldc));
+        if (upd) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const double am = __ldg(a + m + u);
+                v[u].x = fma(-am, b0, v[u].x);
+                v[u].y = fma(-am, b1, v[u].y);
+                __stcs(reinterpret_cast<double2*>(p + (int64_t)u * ldc), v[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            r0 = fma(v[u].x, v[u].x, r0);
+            r1 = fma(v[u].y, v[u].y, r1);
+        }
+        p += 8 * ldc;
+    }
+    for (; m < m1; ++m) {
+        double2 v = __ldcs(reinterpret_cast<const double2*>(p));
+        if (upd) {
+            const double am = __ldg(a + m);
+            v.x = fma(-am, b0, v.x);
+            v.y = fma(-am, b1, v.y);
+            __stcs(reinterpret_cast<double2*>(p), v);
+        }
+        r0 = fma(v.x, v.x, r0);
+        r1 = fma(v.y, v.y, r1);
+        p += ldc;
+    }
+    double* dst = part + (int64_t)blockIdx.y * ldp + c;
+    dst[0] = r0;
+    if (c + 1 < C) dst[1] = r1;
+}
+
+extern "C" int gpx_cov_segments(int64_t M) {
+    int64_t s = (M + 2047) / 2048;
+    if (s < 1) s = 1;
+    if (s > COV_MAX_SEG) s = COV_MAX_SEG;
+    return (int)s;
+}
+
+extern "C" int gpx_cov_update(gpx_handle h, double* cov, int64_t ldc, int64_t M, int64_t C, const double* a, const double* b,
+                              double* partial, int64_t ldp, void* stream) {
+    GPX_REQUIRE(h && cov && partial && M >= 1 && C >= 1, GPX_EINVAL, "bad arguments");
+    GPX_REQUIRE((a == nullptr) == (b == nullptr), GPX_EINVAL, "a and b must both be given or both be NULL");
+    GPX_REQUIRE((ldc % 2) == 0 && ldc >= C + (C & 1) && gpx_aligned16(cov), GPX_EALIGN,
+                "cov must be 16-byte aligned with an even leading dimension");
+    GPX_REQUIRE(b == nullptr || gpx_aligned16(b), GPX_EALIGN, "b must be 16-byte aligned");
+    GPX_REQUIRE(ldp >= C, GPX_EINVAL, "partial rows too short");
+    const int seg = gpx_cov_segments(M);
+    const int64_t rows = (M + seg - 1) / seg;
+    dim3 grid((unsigned)((C + 511) / 512), (unsigned)seg);
+    cov_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cov, ldc, M, C, a, b, rows, partial, ldp);
+    return gpx_check_launch("gpx_cov_update");
+}

@@ -973,6 +973,33 @@ extern "C" int gpx_score_ivar(gpx_handle h, const double* Wm, int64_t ldm, const
     return gpx_argreduce_impl(h, score_out, nullptr, mask, C, 1, best, idx, st);
 }
 
+// IVAR scores from per-segment column sums of squares (resident-covariance mode): same finalisation + arg-min
+extern "C" int gpx_score_ivar_partials(gpx_handle h, const double* partial, int nseg, int64_t ldp, const double* varM, int64_t M,
+                                       const double* varC, int64_t C, double noise, double zero_tol, const uint8_t* mask,
+                                       double* score_out, double* best, int64_t* idx, void* stream) {
+    GPX_REQUIRE(h && partial && varM && varC && score_out && best && idx && nseg >= 1 && M >= 1 && C >= 1, GPX_EINVAL,
+                "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = gpx_sum_impl(h, varM, M, h->scal, st);
+    if (rc) return rc;
+    ivar_finalize_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(partial, nseg, ldp, varC, h->scal, M, C, noise, zero_tol,
+                                                                     score_out);
+    rc = gpx_check_launch("gpx_score_ivar_partials finalize");
+    if (rc) return rc;
+    return gpx_argreduce_impl(h, score_out, nullptr, mask, C, 1, best, idx, st);
+}
+
+// cov[m,c] = k(m,c) - sum_{i<n} Wm[i,m] Wc[i,c] for a GIVEN design (DMMA contraction with the Gram prologue, stored)
+extern "C" int gpx_cov_from_factors(gpx_handle h, const double* Wm, int64_t ldm, const double* Ma_rows, const double* Ma_scal,
+                                    int64_t M, const double* Wc, int64_t ldc, const double* Cb_rows, const double* Cb_scal,
+                                    int64_t C, int64_t n, double* cov, int64_t ldcov, void* stream) {
+    GPX_NEED_KERNEL(h);
+    GPX_REQUIRE(M >= 1 && C >= 1 && n >= 0 && cov && Ma_rows && Ma_scal && Cb_rows && Cb_scal, GPX_EINVAL, "bad arguments");
+    GPX_REQUIRE((M + 63) / 64 <= 65535, GPX_ESIZE, "M too large for one launch");
+    return gpx_launch_core_store(h, Wm, ldm, Ma_rows, Ma_scal, M, Wc, ldc, Cb_rows, Cb_scal, C, n, cov, ldcov,
+                                 (cudaStream_t)stream);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Yard-sticks for bench.py: raw DMMA and DFMA issue rates (no memory traffic)
 // ---------------------------------------------------------------------------------------------

@@ -281,8 +281,12 @@ class GreedyIVAREngine(_Pivoting):
     contraction (K5), takes the arg-min, and appends one row to W_C and W_M."""
 
     def __init__(self, dev: Device, cand: PointSet, mc: PointSet, n_max: int, noise: float, zero_scale: float,
-                 shard=None, index_offset: int = 0):
+                 shard=None, index_offset: int = 0, resident: bool = False):
+        """resident=True keeps the posterior covariance cov_D(m, c) (8*M*C bytes) in HBM and replaces the per-step
+        O(M n C) contraction by one rank-1 update pass (16*M*C bytes of traffic per step, independent of n) -- the
+        better algorithm for a greedy LOOP whenever the matrix fits; scoring a GIVEN design still takes the contraction."""
         self.cand, self.mc = cand, mc
+        self.resident = bool(resident)
         self.noise = float(noise)
         self.zero_tol = ZERO_VAR_TOL * float(zero_scale)
         ncap = max(int(n_max), 1)
@@ -299,12 +303,33 @@ class GreedyIVAREngine(_Pivoting):
         self.workspace = dev.zeros(max(ws, 1))
         self.scores = dev.zeros(cand.ld)
         self.score_trace = None
+        self.cov = None
+        if self.resident:
+            self.nseg = int(lib.gpx_cov_segments(mc.n))
+            self.ldp = (cand.n + 1) & ~1
+            self.cov = dev.empty(mc.n, cand.ld)
+            # cov_0 = K(mc, cand), then the column sums of squares for the first scoring
+            check(lib.gpx_gram(dev.h, ptr(mc.X), mc.n, mc.ld, ptr(cand.X), cand.n, cand.ld, ptr(self.cov), cand.ld, 0, None,
+                               0.0, dev.stream), "gpx_gram")
+            self._cov_pass(None, None)
+            dev.launches += 2
 
     def _local_count(self):
         return self.cand.n
 
+    def _cov_pass(self, a, b):
+        dev, cand, mc = self.dev, self.cand, self.mc
+        check(lib.gpx_cov_update(dev.h, ptr(self.cov), cand.ld, mc.n, cand.n, ptr(a), ptr(b), ptr(self.workspace), self.ldp,
+                                 dev.stream), "gpx_cov_update")
+
     def score(self):
         dev, cand, mc = self.dev, self.cand, self.mc
+        if self.resident:
+            check(lib.gpx_score_ivar_partials(dev.h, ptr(self.workspace), self.nseg, self.ldp, ptr(self.varM), mc.n,
+                                              ptr(self.varC), cand.n, self.noise, self.zero_tol, None, ptr(self.scores),
+                                              ptr(self.best), ptr(self.idx), dev.stream), "gpx_score_ivar_partials")
+            dev.launches += 3
+            return
         ma_rows, ma_scal = mc.side(_lib.SIDE_A)
         cb_rows, cb_scal = cand.side(_lib.SIDE_B)
         check(lib.gpx_score_ivar(dev.h, ptr(self.Wm), mc.ld, ptr(self.varM), ptr(ma_rows), ptr(ma_scal), mc.n,
@@ -322,6 +347,10 @@ class GreedyIVAREngine(_Pivoting):
                                  ptr(self.Wm), mc.ld, self.n, ptr(self.varM), dev.stream), "gpx_append_row")
         dev.launches += 2
         self._record(self.U, self.U.shape[1])
+        if self.resident:
+            # cov -= w_M[n] w_C[n]^T and the next step's column sums of squares, one pass over the resident matrix
+            self._cov_pass(self.Wm[self.n], self.Wc[self.n])
+            dev.launches += 1
         self.n += 1
 
     def force(self, global_index: int):
@@ -329,7 +358,9 @@ class GreedyIVAREngine(_Pivoting):
         self.append()
 
     def snapshot(self):
-        """Cheap save point (running variances + design size); rows >= n of W are never read."""
+        """Cheap save point (running variances + design size); rows >= n of W are never read.
+        Not available in resident mode (the covariance matrix is updated in place)."""
+        assert not self.resident, "resident mode cannot be rolled back"
         return (self.n, self.varC.clone(), self.varM.clone())
 
     def restore(self, snap):
@@ -361,6 +392,15 @@ class GreedyIVAREngine(_Pivoting):
         _, vM = factor.solve_gram(self.mc, W=self.Wm)
         self.varC.copy_(vC)
         self.varM.copy_(vM)
+        if self.resident:
+            dev, cand, mc = self.dev, self.cand, self.mc
+            ma_rows, ma_scal = mc.side(_lib.SIDE_A)
+            cb_rows, cb_scal = cand.side(_lib.SIDE_B)
+            check(lib.gpx_cov_from_factors(dev.h, ptr(self.Wm), mc.ld, ptr(ma_rows), ptr(ma_scal), mc.n, ptr(self.Wc), cand.ld,
+                                           ptr(cb_rows), ptr(cb_scal), cand.n, self.n, ptr(self.cov), cand.ld, dev.stream),
+                  "gpx_cov_from_factors")
+            self._cov_pass(None, None)
+            dev.launches += 2
 
     def step(self):
         self.score()

@@ -281,13 +281,16 @@ def performGreedyVarExperimentalDesign(kernel, mcPoints, nPoints, dimension, wei
     return mcPoints[indKeep, :]
 
 
-def performGreedyIVARExperimentalDesign(costFuncIVAR, candidates, nPoints, returnIndices=False, shard=None):
+def performGreedyIVARExperimentalDesign(costFuncIVAR, candidates, nPoints, returnIndices=False, shard=None, resident=None):
     """Discrete greedy IVAR: at every step score `costFuncIVAR.evaluate(design + [c])` for every candidate
     c and add the arg-min -- what a loop over costFunctionGP_IVAR.evaluate (experimentalDesign.py:79-117)
     computes, restated with the Schur identity and run as one FP64 tensor-core contraction per step.
 
     candidates : (C, d) array.  With `shard` (a gpexp_b200.engine.Shard) every rank passes the FULL
     candidate array and scores its own contiguous block.
+    resident : keep the M x C posterior covariance in HBM and update it by one rank-1 pass per step instead of
+    re-contracting (identical picks, 16*M*C bytes per step instead of 2*M*n*C flop).  None = automatic: on when
+    the matrix takes less than half of the free device memory.
     """
     gp = costFuncIVAR.gaussianProcess
     if costFuncIVAR.space.noiseFunc is not None:
@@ -302,7 +305,16 @@ def performGreedyIVARExperimentalDesign(costFuncIVAR, candidates, nPoints, retur
         lo, hi = Shard.split(candidates.shape[0], shard.world, shard.rank)
     cand = dev.points(candidates[lo:hi])
     mc = dev.points(costFuncIVAR.mcPoints)
-    eng = GreedyIVAREngine(dev, cand, mc, nPoints, float(noise), prior_scale(fam, params), shard=shard, index_offset=lo)
+    if resident is None:
+        import torch
+        free, _ = torch.cuda.mem_get_info(dev.torch_device)
+        resident = 8.0 * mc.n * cand.ld < 0.5 * free
+        if shard is not None and shard.world > 1:  # every rank must take the same path
+            flag = torch.tensor([1 if resident else 0], device=dev.torch_device)
+            shard.dist.all_reduce(flag, op=shard.dist.ReduceOp.MIN, group=shard.group)
+            resident = bool(flag.item())
+    eng = GreedyIVAREngine(dev, cand, mc, nPoints, float(noise), prior_scale(fam, params), shard=shard, index_offset=lo,
+                           resident=bool(resident))
     idx = eng.run(nPoints)
     costFuncIVAR.lastIndices = idx
     costFuncIVAR.lastScores = eng.pick_scores[: eng.n].cpu().numpy()

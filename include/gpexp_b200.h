@@ -178,6 +178,22 @@ int gpx_score_ivar(gpx_handle h, const double* Wm, int64_t ldm, const double* va
                    double zero_tol, const uint8_t* mask, double* workspace, double* score_out, double* best,
                    int64_t* idx, void* stream);
 
+/* ---- Resident posterior covariance: the HBM-bound alternative for greedy IVAR loops -----------
+ * cov (M x ldcov, row m = integration point, 8*M*C bytes resident) holds cov_D(m,c); each greedy step is ONE pass
+ *     cov -= a b^T ,  partial[seg][c] = sum_{m in seg} cov[m,c]^2          (16 B of HBM traffic per pair, any n)
+ * a = new row of W_M (M), b = new row of W_C (C); a = b = NULL only reduces.  partial: gpx_cov_segments(M) x ldp. */
+int gpx_cov_segments(int64_t M);
+int gpx_cov_update(gpx_handle h, double* cov, int64_t ldcov, int64_t M, int64_t C, const double* a, const double* b,
+                   double* partial, int64_t ldp, void* stream);
+/* cov = K(mc, cand) - Wm^T Wc for a given design (DMMA contraction, Gram in the prologue); n = 0 gives K itself. */
+int gpx_cov_from_factors(gpx_handle h, const double* Wm, int64_t ldm, const double* Ma_rows, const double* Ma_scal, int64_t M,
+                         const double* Wc, int64_t ldc, const double* Cb_rows, const double* Cb_scal, int64_t C, int64_t n,
+                         double* cov, int64_t ldcov, void* stream);
+/* IVAR costs + arg-min from the per-segment sums (same finalisation as gpx_score_ivar). */
+int gpx_score_ivar_partials(gpx_handle h, const double* partial, int nseg, int64_t ldp, const double* varM, int64_t M,
+                            const double* varC, int64_t C, double noise, double zero_tol, const uint8_t* mask,
+                            double* score_out, double* best, int64_t* idx, void* stream);
+
 /* K6  MI score = num_var[j] / (1/prec_diag[j] - noise), arg-max over unmasked j
  *     (experimentalDesign.py:259-285 restated: denominator = 1/[(K_SS+noise I)^-1]_yy - noise). */
 int gpx_score_mi(gpx_handle h, const double* num_var, const double* prec_diag, double noise, const uint8_t* mask,
