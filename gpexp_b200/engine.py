@@ -322,9 +322,11 @@ class GreedyIVAREngine(_Pivoting):
         check(lib.gpx_cov_update(dev.h, ptr(self.cov), cand.ld, mc.n, cand.n, ptr(a), ptr(b), ptr(self.workspace), self.ldp,
                                  dev.stream), "gpx_cov_update")
 
-    def score(self):
+    def score(self, contraction: bool = False):
+        """Score every candidate and arg-min.  contraction=True forces the DMMA contraction even in resident mode
+        (cross-check of the two paths on the same state)."""
         dev, cand, mc = self.dev, self.cand, self.mc
-        if self.resident:
+        if self.resident and not contraction:
             check(lib.gpx_score_ivar_partials(dev.h, ptr(self.workspace), self.nseg, self.ldp, ptr(self.varM), mc.n,
                                               ptr(self.varC), cand.n, self.noise, self.zero_tol, None, ptr(self.scores),
                                               ptr(self.best), ptr(self.idx), dev.stream), "gpx_score_ivar_partials")
@@ -332,9 +334,14 @@ class GreedyIVAREngine(_Pivoting):
             return
         ma_rows, ma_scal = mc.side(_lib.SIDE_A)
         cb_rows, cb_scal = cand.side(_lib.SIDE_B)
+        ws = self.workspace
+        if self.resident:  # keep the resident column sums intact: the contraction gets its own scratch
+            if getattr(self, "_ws2", None) is None:
+                self._ws2 = dev.zeros(self.workspace.numel())
+            ws = self._ws2
         check(lib.gpx_score_ivar(dev.h, ptr(self.Wm), mc.ld, ptr(self.varM), ptr(ma_rows), ptr(ma_scal), mc.n,
                                  ptr(self.Wc), cand.ld, ptr(self.varC), ptr(cb_rows), ptr(cb_scal), cand.n, self.n,
-                                 self.noise, self.zero_tol, None, ptr(self.workspace), ptr(self.scores), ptr(self.best),
+                                 self.noise, self.zero_tol, None, ptr(ws), ptr(self.scores), ptr(self.best),
                                  ptr(self.idx), dev.stream), "gpx_score_ivar")
         dev.launches += 4
 

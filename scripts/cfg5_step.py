@@ -21,9 +21,12 @@ sys.path.insert(0, ROOT)
 ap = argparse.ArgumentParser()
 ap.add_argument("--cands", type=int, default=1_000_000)
 ap.add_argument("--mc", type=int, default=100_000)
-ap.add_argument("--n", type=int, default=4096)
+ap.add_argument("--npts", type=int, default=4096)
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--greedy", action="store_true",
+                help="grow the n-point design greedily from the candidates with the resident-covariance engine (the real "
+                     "cfg-5 design) instead of loading a random design; then cross-check the DMMA step on that state")
 args = ap.parse_args()
 
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -37,7 +40,7 @@ from gpexp_b200 import kernels  # noqa: E402
 from gpexp_b200.device import Device  # noqa: E402
 from gpexp_b200.engine import DesignFactor, GreedyIVAREngine, Shard, prior_scale  # noqa: E402
 
-d, n, C, M, noise = 10, args.n, args.cands, args.mc, 1e-6
+d, n, C, M, noise = 10, args.npts, args.cands, args.mc, 1e-6
 rng = np.random.default_rng(5)
 cl = list(np.linspace(0.5, 1.5, d))
 cand_h = rng.uniform(-1, 1, (C, d))
@@ -51,7 +54,8 @@ fam, _, params = kern._gpx_spec()
 shard = Shard() if world > 1 else None
 lo, hi = Shard.split(C, world, rank)
 cand, mc = dev.points(cand_h[lo:hi]), dev.points(mc_h)
-eng = GreedyIVAREngine(dev, cand, mc, n + 1, noise, prior_scale(fam, params), shard=shard, index_offset=lo)
+eng = GreedyIVAREngine(dev, cand, mc, n + 1, noise, prior_scale(fam, params), shard=shard, index_offset=lo,
+                       resident=args.greedy)
 
 
 def sync():
@@ -60,6 +64,51 @@ def sync():
         dist.barrier()
         torch.cuda.synchronize()
 
+
+greedy = None
+if args.greedy:
+    sync()
+    t0 = time.perf_counter()
+    eng.run(n)
+    sync()
+    greedy_s = time.perf_counter() - t0
+    design_idx = eng.indices()[:n]
+    design_h = cand_h[design_idx]
+    # next pick by the resident path, then by the DMMA contraction on the very same state
+    eng.score()
+    res_pick = torch.stack([eng.best.clone(), eng.idx.double() + lo])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.score(contraction=True)
+    sync()
+    e0.record()
+    eng.score(contraction=True)
+    e1.record()
+    sync()
+    dm_ms = e0.elapsed_time(e1)
+    dm_pick = torch.stack([eng.best.clone(), eng.idx.double() + lo])
+    both = torch.cat([res_pick.flatten(), dm_pick.flatten()])
+    if world > 1:
+        allp = [torch.zeros_like(both) for _ in range(world)]
+        dist.all_gather(allp, both)
+        allp = torch.stack(allp).cpu().numpy()
+    else:
+        allp = both.cpu().numpy()[None, :]
+    r_best = allp[np.lexsort((allp[:, 1], allp[:, 0]))[0]]
+    d_best = allp[np.lexsort((allp[:, 3], allp[:, 2]))[0]]
+    greedy = {"greedy_design_s": greedy_s, "greedy_ms_per_step": 1e3 * greedy_s / n,
+              "resident_hbm_gbs_per_gpu": 16.0 * M * (hi - lo) / (greedy_s / n) / 1e9,
+              "next_pick_resident": [float(r_best[0]), int(r_best[1])], "next_pick_dmma": [float(d_best[2]), int(d_best[3])],
+              "dmma_step_ms_on_greedy_design": dm_ms, "dmma_tflops_per_gpu": 2.0 * M * n * (hi - lo) / dm_ms / 1e9,
+              "first_picks": [int(i) for i in design_idx[:8]]}
+    if rank == 0:
+        print(json.dumps({"workload": "cfg-5 greedy design grown with the resident covariance", "n_gpus": world, "n": n, "C": C,
+                          "M": M, **greedy}), flush=True)
+        os.makedirs("gpurun_out", exist_ok=True)
+        json.dump(greedy, open("gpurun_out/cfg5_greedy_N%d.json" % world, "w"), indent=1)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    sys.exit(0)
 
 sync()
 t0 = time.perf_counter()
