@@ -34,6 +34,9 @@
 #ifndef GPX_DEFAULT_IVAR_TN
 #define GPX_DEFAULT_IVAR_TN 8
 #endif
+#ifndef GPX_DEFAULT_IVAR_GROUP
+#define GPX_DEFAULT_IVAR_GROUP 1
+#endif
 
 namespace {
 
@@ -84,7 +87,8 @@ struct CoreArgs {
     int K;
     int dpad;          // prologue K extent, multiple of 4
     int tiles_per_cta; // IVAR: i-tiles each CTA walks
-    int upper_only;
+    int upper_only;    // SUB: skip tiles below the diagonal ; ivar_ws_kernel: candidate tiles per wave group
+    int ldo_splits;    // ivar_ws_kernel: number of M-splits
 };
 
 __device__ __forceinline__ void cp_async16(double* dst, const double* src, bool ok) {
@@ -489,9 +493,21 @@ __global__ void __launch_bounds__(WsCfg<TN>::NT, 1)
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int64_t j0 = (int64_t)blockIdx.x * BN;
+    // Rasterisation for L2 reuse: the 1-D grid is walked as  j-group (one wave of candidate tiles) -> M-split -> tile,
+    // so the waves that share a group's W_C tiles (re-read once per split) run back to back while every wave streams one
+    // W_M slice; DRAM traffic ~ (#groups) x (|W_M| + |W_C group|) instead of (#waves) x (|W_M|/splits + |W_C group|).
+    const int64_t jtiles = (a.J + BN - 1) / BN;
+    const int64_t gw = a.upper_only;  // group width in tiles (reused field: CTAs per wave), >= 1
+    const int64_t per_group = gw * a.ldo_splits;
+    const int64_t jg = blockIdx.x / per_group;
+    const int64_t rem = blockIdx.x - jg * per_group;
+    const int64_t gsz = (jtiles - jg * gw) < gw ? (jtiles - jg * gw) : gw;  // tiles in this (possibly last, short) group
+    const int64_t split = rem / gsz;
+    const int64_t jt = jg * gw + rem % gsz;
+    if (split >= a.ldo_splits) return;  // padding CTAs of a short last group
+    const int64_t j0 = jt * BN;
     const int64_t itiles = (a.I + BM - 1) / BM;
-    const int64_t it_begin = (int64_t)blockIdx.y * a.tiles_per_cta;
+    const int64_t it_begin = split * a.tiles_per_cta;
     int64_t it_end = it_begin + a.tiles_per_cta;
     if (it_end > itiles) it_end = itiles;
     const int ntiles = it_end > it_begin ? (int)(it_end - it_begin) : 0;
@@ -854,9 +870,22 @@ int gpx_launch_core_ivar(gpx_handle h, const double* Wm, int64_t ldm, const doub
     a.dpad = (h->kp.d + 3) & ~3;
     a.tiles_per_cta = (int)((itl + splits - 1) / splits);
     a.upper_only = 0;
+    a.ldo_splits = 0;
     *nsplit_out = splits;
     if (tma) {
-        dim3 grid((unsigned)((C + BN - 1) / BN), (unsigned)splits);
+        const int64_t jt = (C + BN - 1) / BN;
+        static int gmul = 0;
+        if (gmul == 0) {
+            const char* e = getenv("GPX_IVAR_GROUP");
+            gmul = (e && e[0] >= '1' && e[0] <= '8') ? (e[0] - '0') : GPX_DEFAULT_IVAR_GROUP;
+        }
+        // one CTA per SM: a group is `gmul` waves of candidate tiles (their W_C tiles must stay L2-resident)
+        const int64_t gw = (int64_t)gmul * (h->sm_count > 0 ? h->sm_count : 148);
+        const int64_t groups = (jt + gw - 1) / gw;
+        a.upper_only = (int)gw;
+        a.ldo_splits = splits;
+        // every group gets gw*splits CTA slots; the short last group leaves some idle (they exit at once)
+        dim3 grid((unsigned)(groups * gw * splits), 1u);
         GPX_DISPATCH_FAMILY(h->kp.family, rc = (launch_ivar_ws<FAM>(a, h->kp, grid, st)));
         return rc;
     }
@@ -892,6 +921,7 @@ int gpx_launch_core_store(gpx_handle h, const double* A, int64_t lda, const doub
     a.dpad = (h->kp.d + 3) & ~3;
     a.tiles_per_cta = 1;
     a.upper_only = 0;
+    a.ldo_splits = 0;
     GPX_DISPATCH_FAMILY(h->kp.family,
                         rc = (launch_core<FAM, EPI_STORE, true>(a, h->kp, (J + BN - 1) / BN, (I + core_bm() - 1) / core_bm(), st)));
     return rc;
@@ -922,6 +952,7 @@ extern "C" int gpx_dgemm_tn_sub(gpx_handle h, const double* A, int64_t lda, cons
     a.dpad = 0;
     a.tiles_per_cta = 1;
     a.upper_only = upper_only;
+    a.ldo_splits = 0;
     KParams kp = h->kp;
     return launch_core<GPX_SE, EPI_SUB, false>(a, kp, (J + BN - 1) / BN, (I + core_bm() - 1) / core_bm(), (cudaStream_t)stream);
 }
