@@ -529,6 +529,9 @@ class ShardedMIEngine(_Pivoting):
         rank = shard.rank if shard is not None else 0
         V = pool_host.shape[0]
         self.V = V
+        # keep at least ~4 elimination blocks per rank so that the column ranges stay balanced on small pools
+        while self.BLK > 128 and (V + self.BLK - 1) // self.BLK < 4 * world:
+            self.BLK //= 2
         nblk = (V + self.BLK - 1) // self.BLK
         self.bounds = [min(Shard.split(nblk, world, r)[0] * self.BLK, V) for r in range(world)] + [V]
         lo, hi = self.bounds[rank], self.bounds[rank + 1]
@@ -614,7 +617,11 @@ class ShardedMIEngine(_Pivoting):
     def score(self):
         dev = self.dev
         nloc = self.hi - self.lo
-        check(lib.gpx_score_mi(dev.h, ptr(self.num), ptr(self.pd), self.noise, ptr(self.mask), max(nloc, 1), ptr(self.scores),
+        if nloc == 0:  # a rank without columns (more ranks than blocks) only takes part in the exchanges
+            self.idx.fill_(-1)
+            self.best.zero_()
+            return
+        check(lib.gpx_score_mi(dev.h, ptr(self.num), ptr(self.pd), self.noise, ptr(self.mask), nloc, ptr(self.scores),
                                ptr(self.best), ptr(self.idx), dev.stream), "gpx_score_mi")
         dev.launches += 2
 
@@ -628,16 +635,19 @@ class ShardedMIEngine(_Pivoting):
         check(lib.gpx_local_index(dev.h, ptr(self.rec_win), self.lo, nloc, ptr(self.loc2), st), "gpx_local_index")
         self.buf.zero_()
         bufY, bufU = self.buf[: self.bufY_len], self.buf[self.bufY_len:]
-        check(lib.gpx_gather_column(dev.h, ptr(self.Y), ld, V, ptr(self.pd), ptr(self.loc2), ptr(bufY), st), "gpx_gather_column")
-        check(lib.gpx_gather_column(dev.h, ptr(self.Us), ld, self.n, ptr(self.pd), ptr(self.loc2), ptr(bufU), st),
-              "gpx_gather_column")
+        if nloc > 0:
+            check(lib.gpx_gather_column(dev.h, ptr(self.Y), ld, V, ptr(self.pd), ptr(self.loc2), ptr(bufY), st),
+                  "gpx_gather_column")
+            check(lib.gpx_gather_column(dev.h, ptr(self.Us), ld, self.n, ptr(self.pd), ptr(self.loc2), ptr(bufU), st),
+                  "gpx_gather_column")
         if self.rec_all is not None:
             self.dist.all_reduce(self.buf, op=self.dist.ReduceOp.SUM, group=self.shard.group)
-        check(lib.gpx_mi_prec_column(dev.h, ptr(self.Y), V, nloc, ld, self.lo, ptr(self.loc2) + 8, ptr(bufY) + 8 * HDR,
-                                     ptr(self.pws), ptr(self.pcol), st), "gpx_mi_prec_column")
-        check(lib.gpx_append_row(dev.h, _lib.ROW_MATRIX, ptr(bufU), ptr(self.pcol), None, nloc, ld, ptr(self.Us), ld, self.n,
-                                 ptr(self.pd), st), "gpx_append_row")
-        check(lib.gpx_set_mask(dev.h, ptr(self.mask), ptr(self.loc2), 1, st), "gpx_set_mask")
+        if nloc > 0:
+            check(lib.gpx_mi_prec_column(dev.h, ptr(self.Y), V, nloc, ld, self.lo, ptr(self.loc2) + 8, ptr(bufY) + 8 * HDR,
+                                         ptr(self.pws), ptr(self.pcol), st), "gpx_mi_prec_column")
+            check(lib.gpx_append_row(dev.h, _lib.ROW_MATRIX, ptr(bufU), ptr(self.pcol), None, nloc, ld, ptr(self.Us), ld,
+                                     self.n, ptr(self.pd), st), "gpx_append_row")
+            check(lib.gpx_set_mask(dev.h, ptr(self.mask), ptr(self.loc2), 1, st), "gpx_set_mask")
         dev.launches += 9
         self._record()
         self.n += 1
