@@ -724,7 +724,7 @@ __global__ void __launch_bounds__(WsCfg<TN>::NT, 1)
     __syncthreads();
     if (tid < BN && j0 + tid < a.J) {
         const double r = ((s_red[tid] + s_red[BN + tid]) + s_red[2 * BN + tid]) + s_red[3 * BN + tid];
-        a.out[(int64_t)blockIdx.y * a.ldo + j0 + tid] = r;
+        a.out[split * a.ldo + j0 + tid] = r;
     }
 }
 
