@@ -255,20 +255,25 @@ def performGreedyMIExperimentalDesign(costFuncMI, nPoints, start=0, shard=None):
     return costFuncMI.mcPoints[idx, :]
 
 
-def performGreedyVarExperimentalDesign(kernel, mcPoints, nPoints, dimension, weights=None, indKeepStart=[]):
+def performGreedyVarExperimentalDesign(kernel, mcPoints, nPoints, dimension, weights=None, indKeepStart=[], shard=None):
     """Greedy maximum-posterior-variance design (experimentalDesign.py:787-845).
 
     Same contract as the reference: returns mcPoints[indKeep, :]; `indKeepStart` seeds the design and
     is extended in place (the reference mutates the caller's list, :808); selected points stay in the
-    pool; the nugget is 0.0 (:825).
+    pool; the nugget is 0.0 (:825).  Extension: with `shard` (gpexp_b200.engine.Shard) every rank passes the full
+    pool and works on its own contiguous block; all ranks return the same design.
     """
     if indKeepStart == []:
         indKeep = []
     else:
         indKeep = indKeepStart
     dev = kernel._bind()
-    pool = dev.points(mcPoints)
-    eng = GreedyVarEngine(dev, pool, max(nPoints, len(indKeep)), weights=weights, noise=0.0)
+    lo, hi = 0, mcPoints.shape[0]
+    if shard is not None:
+        lo, hi = Shard.split(mcPoints.shape[0], shard.world, shard.rank)
+    pool = dev.points(mcPoints[lo:hi])
+    eng = GreedyVarEngine(dev, pool, max(nPoints, len(indKeep)), weights=None if weights is None else weights[lo:hi],
+                          noise=0.0, shard=shard, index_offset=lo)
     for seed in list(indKeep):
         eng.force(int(seed))
 

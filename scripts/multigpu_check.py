@@ -34,9 +34,8 @@ def main():
     pool = rng.uniform(-1, 1, (10007, 5))
     mk = kernels.KernelIsoMatern(1.0, 1.0, 5)
     dev = mk._bind()
-    lo, hi = Shard.split(pool.shape[0], world, rank)
-    eng = GreedyVarEngine(dev, dev.points(pool[lo:hi]), 25, shard=shard, index_offset=lo)
-    vidx = eng.run(25)
+    vpts = ed.performGreedyVarExperimentalDesign(mk, pool, 25, 5, shard=shard)   # public API, pool sharded inside
+    vidx = [int(np.where(np.all(pool == p, axis=1))[0][0]) for p in vpts]
     # --- greedy mutual information, |V| x |V| matrices sharded by column blocks ------------------------
     from gpexp_b200.engine import ShardedMIEngine
     vpool = rng.standard_normal((1500, 3))

