@@ -4,8 +4,6 @@ from typing import Callable, Optional
 
 
 class Space:
-    __slots__ = ("dimension", "inBoundsBool", "sample", "probDensity", "noiseFunc")
-
     def __init__(self, dimensionIn: int, samplerIn: Optional[Callable], probDensityIn: Optional[Callable],
                  noise: Optional[Callable] = None):
         # positional order and attribute names are the reference's; nothing else lives here
