@@ -53,6 +53,7 @@ SIGNATURES = {
     "gpx_trsm_back": [_p, _p, _i64, _i64, _p, _i64, _i64, _p],
     "gpx_trtri_t": [_p, _p, _i64, _i64, _p, _i64, _p],
     "gpx_dgemm_tn_sub": [_p, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _int, _p],
+    "gpx_dgemm_tn_sub_padded": [_p, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _int, _p],
     "gpx_gather_pivot": [_p, _p, _i64, _i64, _p, _p, _i64, _p, _p, _i64, _dbl, _p, _p],
     "gpx_select_pivot": [_p, _p, _int, _i64, _i64, _int, _p, _p],
     "gpx_append_row": [_p, _int, _p, _p, _p, _i64, _i64, _p, _i64, _i64, _p, _p],

@@ -736,6 +736,127 @@ bool ivar_use_tma() {
     }
     return v == 1;
 }
+// ---------------------------------------------------------------------------------------------
+// TMA + mbarrier variant of the plain update  C[i,j] -= sum_k A[k,i] B[k,j]  for callers that GUARANTEE fully padded
+// operands (every 128-wide tile of A and B readable and finite; the distributed MI set-up does).  Same ring, fragment
+// layout and rotating producer as ivar_ws_kernel, one 128x128 tile per CTA, no prologue.
+// ---------------------------------------------------------------------------------------------
+constexpr int SUBWS_SMEM_DOUBLES = WS_STAGES * WS_STAGE + 2 * WS_STAGES;
+constexpr size_t SUBWS_SMEM_BYTES = (size_t)SUBWS_SMEM_DOUBLES * sizeof(double);
+
+__global__ void __launch_bounds__(256, 1) sub_ws_kernel(const __grid_constant__ CoreArgs a) {
+    constexpr int BM = WS_BM, LD = WS_LD, NW = 8;
+    extern __shared__ __align__(16) double smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + WS_STAGES * WS_STAGE);
+    uint64_t* empty = full + WS_STAGES;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int64_t j0 = (int64_t)blockIdx.x * BN;
+    const int64_t i0 = (int64_t)blockIdx.y * BM;
+    if (a.upper_only && i0 >= j0 + BN) return;  // tile strictly below the diagonal of a symmetric update
+    const int G = (a.K + WS_BK - 1) / WS_BK;     // chunks
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < WS_STAGES; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, NW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const int wm = warp & 3, wn = warp >> 2;
+    const int g4 = lane >> 2, q4 = lane & 3;
+
+    auto produce = [&](int c) {
+        if (c >= G) return;
+        const int s = c % WS_STAGES;
+        const unsigned int ph = (unsigned int)(c / WS_STAGES) & 1u;
+        mbar_wait(empty + s, ph ^ 1u);
+        const double* srcA = a.A + (int64_t)c * WS_BK * a.lda + i0;
+        const double* srcB = a.B + (int64_t)c * WS_BK * a.ldb + j0;
+        const int rem = a.K - c * WS_BK;
+        const int krows = rem < WS_BK ? rem : WS_BK;
+        const int ksteps = rem >= WS_BK ? WS_KSTEPS : ((rem + 3) >> 2);
+        double* stA = smem + s * WS_STAGE;
+        double* stB = stA + WS_BK * LD;
+        if (krows < ksteps * 4) {
+            for (int r = krows; r < ksteps * 4; ++r) {
+                for (int cc = lane * 2; cc < BM; cc += 64) {
+                    *reinterpret_cast<double2*>(stA + r * LD + cc) = make_double2(0.0, 0.0);
+                    *reinterpret_cast<double2*>(stB + r * LD + cc) = make_double2(0.0, 0.0);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            __syncwarp();
+        }
+        if (lane == 0) {
+            mbar_arrive_expect_tx(full + s, (unsigned int)krows * (BM + BN) * 8u);
+#pragma unroll 4
+            for (int r = 0; r < krows; ++r) {
+                bulk_g2s(stA + r * LD, srcA + (int64_t)r * a.lda, BM * 8u, full + s);
+                bulk_g2s(stB + r * LD, srcB + (int64_t)r * a.ldb, BN * 8u, full + s);
+            }
+        }
+        __syncwarp();
+    };
+    if (warp < WS_AHEAD) produce(warp);
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
+    double af0[4], bf0[8];
+    const int fa = q4 * LD + wm * 32 + g4 * 2;
+    const int fb = WS_BK * LD + q4 * LD + wn * 64 + g4 * 2;
+    for (int g = 0; g < G; ++g) {
+        const int s = g % WS_STAGES;
+        const unsigned int ph = (unsigned int)(g / WS_STAGES) & 1u;
+        if (warp == (g & (NW - 1))) produce(g + WS_AHEAD);
+        mbar_wait(full + s, ph);
+        const double* pa = smem + s * WS_STAGE + fa;
+        const double* pb = smem + s * WS_STAGE + fb;
+        const int rem = a.K - g * WS_BK;
+        const int ksteps = rem >= WS_BK ? WS_KSTEPS : ((rem + 3) >> 2);
+#pragma unroll 1
+        for (int ks = 0; ks < ksteps; ++ks) {
+            load_frags_ws<8>(af0, bf0, pa, pb, ks);
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) dmma(acc[t][u][0], acc[t][u][1], af0[t], bf0[u]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+    }
+    // C -= acc, two adjacent columns per 16-byte access
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int64_t i = i0 + wm * 32 + (t >> 1) * 16 + g4 * 2 + (t & 1);
+        if (i >= a.I) continue;
+#pragma unroll
+        for (int u2 = 0; u2 < 4; ++u2)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int64_t j = j0 + wn * 64 + u2 * 16 + (q4 * 2 + e) * 2;
+                if (j >= a.J) continue;
+                double* dst = a.out + i * a.ldo + j;
+                const double v0 = acc[t][u2 * 2][e], v1 = acc[t][u2 * 2 + 1][e];
+                if (j + 1 < a.J) {
+                    double2 c = *reinterpret_cast<double2*>(dst);
+                    c.x -= v0;
+                    c.y -= v1;
+                    *reinterpret_cast<double2*>(dst) = c;
+                } else {
+                    dst[0] -= v0;
+                }
+            }
+    }
+}
+
 int ivar_tn() {
     static int v = 0;
     if (v == 0) {
@@ -955,6 +1076,55 @@ extern "C" int gpx_dgemm_tn_sub(gpx_handle h, const double* A, int64_t lda, cons
     a.ldo_splits = 0;
     KParams kp = h->kp;
     return launch_core<GPX_SE, EPI_SUB, false>(a, kp, (J + BN - 1) / BN, (I + core_bm() - 1) / core_bm(), (cudaStream_t)stream);
+}
+
+// Same update for operands the CALLER guarantees to be fully padded (every 128-wide tile of A's I columns and B's J
+// columns readable and finite, lda/ldb multiples of 128 or at least covering the rounded-up extents): TMA + mbarrier kernel.
+extern "C" int gpx_dgemm_tn_sub_padded(gpx_handle h, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                                       int64_t ldc, int64_t I, int64_t J, int64_t K, int upper_only, void* stream) {
+    GPX_REQUIRE(h != nullptr, GPX_EINVAL, "handle is NULL");
+    GPX_REQUIRE(I >= 0 && J >= 0 && K >= 0, GPX_EINVAL, "negative size");
+    if (I == 0 || J == 0 || K == 0) return GPX_OK;
+    GPX_REQUIRE(A && B && C, GPX_EINVAL, "NULL pointer");
+    GPX_REQUIRE((I + WS_BM - 1) / WS_BM <= 65535, GPX_ESIZE, "I too large for one launch");
+    int rc;
+    if ((rc = check_operand(A, lda, "A"))) return rc;
+    if ((rc = check_operand(B, ldb, "B"))) return rc;
+    if ((rc = check_operand(C, ldc, "C"))) return rc;
+    GPX_REQUIRE(lda >= (I + WS_BM - 1) / WS_BM * WS_BM && ldb >= (J + BN - 1) / BN * BN, GPX_EALIGN,
+                "padded variant needs leading dimensions that cover whole 128-wide tiles");
+    static const bool use_tma = []() {
+        const char* e = getenv("GPX_SUB_TMA");
+        return !(e && e[0] == '0');
+    }();
+    if (!use_tma) return gpx_dgemm_tn_sub(h, A, lda, B, ldb, C, ldc, I, J, K, upper_only, stream);
+    CoreArgs a;
+    a.A = A;
+    a.B = B;
+    a.Ap = a.Bp = a.As = a.Bs = nullptr;
+    a.out = C;
+    a.lda = lda;
+    a.ldb = ldb;
+    a.ldo = ldc;
+    a.I = I;
+    a.J = J;
+    a.K = (int)K;
+    a.dpad = 0;
+    a.tiles_per_cta = 1;
+    a.upper_only = upper_only;
+    a.ldo_splits = 0;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(sub_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SUBWS_SMEM_BYTES);
+        if (e != cudaSuccess) {
+            gpx_set_error("sub_ws: cannot opt in to %zu bytes of shared memory: %s", SUBWS_SMEM_BYTES, cudaGetErrorString(e));
+            return (int)e;
+        }
+        configured = true;
+    }
+    dim3 grid((unsigned)((J + BN - 1) / BN), (unsigned)((I + WS_BM - 1) / WS_BM));
+    sub_ws_kernel<<<grid, 256, SUBWS_SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    return gpx_check_launch("gpx_dgemm_tn_sub_padded");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -571,12 +571,13 @@ class ShardedMIEngine(_Pivoting):
                     dist.broadcast(panel[:kb], src=owner, group=group)
                 cu = max(lo, kb) - lo
                 if nloc - cu > 0:
-                    check(lib.gpx_dgemm_tn_sub(dev.h, ptr(panel), B, ptr(A) + 8 * cu, ld, ptr(A) + 8 * (kb * ld + cu), ld, b,
-                                               nloc - cu, kb, 0, st), "gpx_dgemm_tn_sub")
+                    # panel, A and Y are allocated in whole 128-wide tiles: the TMA update kernel may read full tiles
+                    check(lib.gpx_dgemm_tn_sub_padded(dev.h, ptr(panel), B, ptr(A) + 8 * cu, ld, ptr(A) + 8 * (kb * ld + cu), ld,
+                                                      b, nloc - cu, kb, 0, st), "gpx_dgemm_tn_sub_padded")
                 ny = min(hi, kb + b) - lo
                 if ny > 0:
-                    check(lib.gpx_dgemm_tn_sub(dev.h, ptr(panel), B, ptr(Y), ld, ptr(Y) + 8 * kb * ld, ld, b, ny, kb, 0, st),
-                          "gpx_dgemm_tn_sub")
+                    check(lib.gpx_dgemm_tn_sub_padded(dev.h, ptr(panel), B, ptr(Y), ld, ptr(Y) + 8 * kb * ld, ld, b, ny, kb, 0,
+                                                      st), "gpx_dgemm_tn_sub_padded")
             if mine:
                 check(lib.gpx_potrf(dev.h, ptr(A) + 8 * (kb * ld + kb - lo), b, ld, ptr(info), st), "gpx_potrf")
                 bad.copy_(torch.maximum(bad, torch.where(info > 0, info + kb, info)))

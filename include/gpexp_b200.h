@@ -130,6 +130,12 @@ int gpx_trtri_t(gpx_handle h, const double* U, int64_t n, int64_t ldu, double* Y
 int gpx_dgemm_tn_sub(gpx_handle h, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                      int64_t ldc, int64_t I, int64_t J, int64_t K, int upper_only, void* stream);
 
+/* The same update on the TMA + mbarrier kernel, for callers that GUARANTEE fully padded operands: every 128-wide tile
+ * covering A's I columns and B's J columns is readable and finite (lda >= roundup(I,128), ldb >= roundup(J,128) counted
+ * from the pointers handed in).  Used by the column-sharded MI set-up. */
+int gpx_dgemm_tn_sub_padded(gpx_handle h, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                            int64_t ldc, int64_t I, int64_t J, int64_t K, int upper_only, void* stream);
+
 /* Pivot record: what one greedy step needs to know about the chosen point.  Layout (doubles):
  *   [0] score  [1] global index (exact integer < 2^53)  [2] var_D(p) + noise (the squared divisor)
  *   [3 .. 3+GPX_MAX_DIM) coordinates of x_p   [GPX_PIVOT_HDR .. GPX_PIVOT_HDR + n) column W[0..n, p]   */

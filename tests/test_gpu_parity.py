@@ -704,3 +704,25 @@ def test_resident_covariance_mode_equals_contraction_mode(gx):
         e3.append()
         e3.score()
         assert int(e3.idx.item()) == int(i1[8])
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (3, 130, 5), (129, 257, 33), (260, 131, 200), (512, 700, 1000), (128, 128, 32)])
+def test_dgemm_tn_sub_padded_tma_kernel(gx, shape):
+    """The TMA + mbarrier update kernel (fully padded operands) against numpy, ragged I / J / K and the symmetric mode."""
+    I, J, K = shape
+    rng = np.random.default_rng(I * 7 + J)
+    dev, lib, ptr = gx.dev, gx.lib, gx.ptr
+    A, B, Cm = rng.standard_normal((K, I)), rng.standard_normal((K, J)), rng.standard_normal((I, J))
+    lda, ldb, ldc = gx.device.roundup(I), gx.device.roundup(J), gx.device.roundup(J)
+    Ad, Bd, Cd = dev.zeros(K, lda), dev.zeros(K, ldb), dev.zeros(I, ldc)
+    Ad[:, :I], Bd[:, :J], Cd[:, :J] = dev.upload(A), dev.upload(B), dev.upload(Cm)
+    gx.check(lib.gpx_dgemm_tn_sub_padded(dev.h, ptr(Ad), lda, ptr(Bd), ldb, ptr(Cd), ldc, I, J, K, 0, dev.stream))
+    np.testing.assert_allclose(Cd[:, :J].cpu().numpy(), Cm - A.T @ B, rtol=1e-12, atol=1e-12)
+    assert np.all(Cd[:, J:].cpu().numpy() == 0.0)
+    if I == J:
+        Cd[:, :J] = dev.upload(Cm)
+        gx.check(lib.gpx_dgemm_tn_sub_padded(dev.h, ptr(Ad), lda, ptr(Ad), lda, ptr(Cd), ldc, I, I, K, 1, dev.stream))
+        got, want = Cd[:, :J].cpu().numpy(), Cm - A.T @ A
+        np.testing.assert_allclose(np.triu(got), np.triu(want), rtol=1e-12, atol=1e-12)
+    # unpadded leading dimension is refused
+    assert lib.gpx_dgemm_tn_sub_padded(dev.h, ptr(Ad), 2, ptr(Bd), ldb, ptr(Cd), ldc, max(I, 3), J, K, 0, dev.stream) == -2
