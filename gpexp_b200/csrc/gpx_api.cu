@@ -5,7 +5,10 @@
 
 #include "gpx_common.cuh"
 
+#include <atomic>
+
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};  // kernel launches issued by this library (every launch site checks once)
 
 void gpx_set_error(const char* fmt, ...) {
     va_list ap;
@@ -15,6 +18,7 @@ void gpx_set_error(const char* fmt, ...) {
 }
 
 int gpx_check_launch(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         gpx_set_error("%s: %s", what, cudaGetErrorString(e));
@@ -23,7 +27,25 @@ int gpx_check_launch(const char* what) {
     return GPX_OK;
 }
 
+int gpx_ensure_smem(gpx_handle h, const void* func, size_t bytes, const char* name) {
+    for (int i = 0; i < h->n_smem_ready; ++i)
+        if (h->smem_ready[i] == func) return GPX_OK;
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != h->device) cudaSetDevice(h->device);
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (cur != h->device && cur >= 0) cudaSetDevice(cur);
+    if (e != cudaSuccess) {
+        gpx_set_error("%s: cannot opt in to %zu bytes of shared memory: %s", name, bytes, cudaGetErrorString(e));
+        return (int)e;
+    }
+    if (h->n_smem_ready < GPX_SMEM_FUNCS) h->smem_ready[h->n_smem_ready++] = func;
+    return GPX_OK;
+}
+
 extern "C" int gpx_version(void) { return GPX_VERSION; }
+
+extern "C" int64_t gpx_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 extern "C" const char* gpx_last_error(void) { return g_err; }
 
@@ -119,5 +141,6 @@ extern "C" int gpx_set_kernel(gpx_handle h, int family, int d, const double* p, 
     }
     h->kp = kp;
     h->has_kernel = true;
+    memset(h->center, 0, sizeof(h->center));  // a centre belongs to one kernel / data set
     return GPX_OK;
 }

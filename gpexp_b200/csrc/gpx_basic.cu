@@ -117,48 +117,86 @@ extern "C" int gpx_gram(gpx_handle h, const double* X, int64_t nx, int64_t ldx, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Prepared side for the tensor-core Gram prologue.
-//   SE      e = -1/2 sum a (x-y)^2      = [-1/2 sum a x^2] + [-1/2 sum a y^2] + sum (a x) y
-//   MATERN  q = sum (x-y)^2             = [sum x^2] + [sum y^2] + sum (-2 x) y
-//   MEHLER  e = -sum c (a x^2 - b x y + a y^2) = [-sum c a x^2] + [-sum c a y^2] + sum (c b x) y
+// Prepared side for the tensor-core Gram prologue: k = f(e), e = sum over the d+2 rows of  A-row(i) * B-row(j).
+//   SE      e = -1/2 sum a (x-y)^2        rows q<d: (a_q x_q) * y_q ;  alpha = -1/2 sum a x^2 ;  beta = -1/2 sum a y^2
+//   MATERN  e = sum (x-y)^2               rows q<d: (-2 x_q) * y_q   ;  alpha = sum x^2        ;  beta = sum y^2
+//   MEHLER  e = -sum c (a x^2 - b x y + a y^2)   rows q<d: (c b x_q) * y_q ; alpha = -sum c a x^2 ; beta = -sum c a y^2
+//   row d   : alpha_i on side A, 1 on side B       row d+1 : 1 on side A, beta_j on side B       rows > d+1 : 0
+// For the stationary families the handle's centre is subtracted from every coordinate first (the kernel only sees
+// x - y), which keeps |alpha|, |beta| -- the terms that cancel against sum u v -- as small as the data allow.
+// maxabs (nullable): max_j |alpha_j| resp. |beta_j|, the number the host checks before trusting this form.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) prep_side_kernel(const __grid_constant__ KParams kp, int side,
-                                                         const double* __restrict__ X, int64_t n, int64_t ldx,
-                                                         double* __restrict__ rows, double* __restrict__ scal, int64_t ld) {
+__global__ void __launch_bounds__(256) prep_side_kernel(const __grid_constant__ KParams kp, const __grid_constant__ KCenter ctr,
+                                                         int side, const double* __restrict__ X, int64_t n, int64_t ldx,
+                                                         double* __restrict__ rows, int64_t ld,
+                                                         unsigned long long* __restrict__ maxabs) {
     const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (j >= ld) return;
     double s = 0.0;
+    if (j < ld) {
+        const bool live = j < n;
 #pragma unroll
-    for (int i = 0; i < GPX_KROWS; ++i) {
-        double r = 0.0;
-        if (i < kp.d && j < n) {
-            const double x = X[i * ldx + j];
-            if (kp.family == GPX_SE) {
-                s = fma(x * x, kp.a[i], s);
-                r = side == GPX_SIDE_A ? x * kp.a[i] : x;
-            } else if (kp.family == GPX_MATERN32) {
-                s = fma(x, x, s);
-                r = side == GPX_SIDE_A ? -2.0 * x : x;
-            } else {
-                s = fma(x * x, kp.c[i] * kp.a[i], s);
-                r = side == GPX_SIDE_A ? kp.c[i] * kp.b[i] * x : x;
+        for (int i = 0; i < GPX_KROWS; ++i) {
+            double r = 0.0;
+            if (i < kp.d && live) {
+                double x = X[i * ldx + j];
+                if (kp.family == GPX_SE) {
+                    x -= ctr.c[i];
+                    s = fma(x * x, kp.a[i], s);
+                    r = side == GPX_SIDE_A ? x * kp.a[i] : x;
+                } else if (kp.family == GPX_MATERN32) {
+                    x -= ctr.c[i];
+                    s = fma(x, x, s);
+                    r = side == GPX_SIDE_A ? -2.0 * x : x;
+                } else {
+                    s = fma(x * x, kp.c[i] * kp.a[i], s);
+                    r = side == GPX_SIDE_A ? kp.c[i] * kp.b[i] * x : x;
+                }
             }
+            if (i < kp.d) rows[i * ld + j] = r;
         }
-        rows[i * ld + j] = r;
+        if (kp.family == GPX_SE) s *= -0.5;
+        if (kp.family == GPX_MEHLER) s = -s;
+        if (!live) s = 0.0;
+        const double one = live ? 1.0 : 0.0;
+        rows[(int64_t)kp.d * ld + j] = side == GPX_SIDE_A ? s : one;
+        rows[(int64_t)(kp.d + 1) * ld + j] = side == GPX_SIDE_A ? one : s;
+        for (int i = kp.d + 2; i < GPX_KROWS; ++i) rows[(int64_t)i * ld + j] = 0.0;
     }
-    if (kp.family == GPX_SE) s *= -0.5;
-    if (kp.family == GPX_MEHLER) s = -s;
-    scal[j] = j < n ? s : 0.0;
+    if (maxabs) {
+        double m = fabs(s);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+        // non-negative doubles order like their bit patterns
+        if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(maxabs, (unsigned long long)__double_as_longlong(m));
+    }
 }
 
-extern "C" int gpx_prep_side(gpx_handle h, int side, const double* X, int64_t n, int64_t ldx, double* rows, double* scal,
-                             int64_t ld, void* stream) {
+extern "C" int gpx_set_center(gpx_handle h, const double* center_host) {
+    GPX_REQUIRE(h != nullptr, GPX_EINVAL, "handle is NULL");
+    for (int i = 0; i < GPX_MAX_DIM; ++i) h->center[i] = (center_host && h->has_kernel && i < h->kp.d) ? center_host[i] : 0.0;
+    return GPX_OK;
+}
+
+extern "C" int gpx_prep_side(gpx_handle h, int side, const double* X, int64_t n, int64_t ldx, double* rows, int64_t ld,
+                             double* maxabs, void* stream) {
     GPX_NEED_KERNEL(h);
     GPX_REQUIRE(side == GPX_SIDE_A || side == GPX_SIDE_B, GPX_EINVAL, "bad side");
     GPX_REQUIRE(n >= 0 && ld >= n, GPX_EINVAL, "bad sizes");
+    GPX_REQUIRE(h->kp.d + 2 <= GPX_KROWS, GPX_ESIZE, "the expanded form carries d + 2 rows: d <= GPX_KROWS - 2");
     if (ld == 0) return GPX_OK;
-    GPX_REQUIRE(rows && scal && (X || n == 0), GPX_EINVAL, "NULL pointer");
-    prep_side_kernel<<<(unsigned)((ld + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->kp, side, X, n, ldx, rows, scal, ld);
+    GPX_REQUIRE(rows && (X || n == 0), GPX_EINVAL, "NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (maxabs) {
+        cudaError_t e = cudaMemsetAsync(maxabs, 0, sizeof(double), st);
+        if (e != cudaSuccess) {
+            gpx_set_error("gpx_prep_side: cudaMemsetAsync: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+    }
+    KCenter ctr;
+    for (int i = 0; i < GPX_MAX_DIM; ++i) ctr.c[i] = h->center[i];
+    prep_side_kernel<<<(unsigned)((ld + 255) / 256), 256, 0, st>>>(h->kp, ctr, side, X, n, ldx, rows, ld,
+                                                                  reinterpret_cast<unsigned long long*>(maxabs));
     return gpx_check_launch("gpx_prep_side");
 }
 
@@ -364,7 +402,9 @@ __global__ void __launch_bounds__(128) append_row_kernel(const __grid_constant__
         s0 = s.x;
         s1 = s.y;
     }
-    const double lnn = sqrt(rec[2]);
+    // a non-positive pivot (numerically dependent point, noise 0) appends a zero row: "no reduction", what the
+    // reference's pinv makes of a null direction (gp.py:181) -- instead of NaN from sqrt of a negative number
+    const double lnn = rec[2] > 0.0 ? sqrt(rec[2]) : INFINITY;
     const double w0 = (s0 - a0) / lnn;
     const double w1 = (s1 - a1) / lnn;
     const bool two = j + 1 < ncols;
@@ -397,8 +437,10 @@ extern "C" int gpx_append_row(gpx_handle h, int row_source, const double* rec, c
     const unsigned grid = (unsigned)((ncols + 255) / 256);
 #define GPX_APPEND_LAUNCH(F, S)                                                                                      \
     do {                                                                                                             \
-        if (smem > 48 * 1024)                                                                                        \
-            cudaFuncSetAttribute(append_row_kernel<F, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   \
+        if (smem > 48 * 1024) {                                                                                      \
+            const int rc_ = gpx_ensure_smem(h, (const void*)append_row_kernel<F, S>, 200 * 1024, "append_row");      \
+            if (rc_) return rc_;                                                                                     \
+        }                                                                                                            \
         append_row_kernel<F, S><<<grid, 128, smem, st>>>(h->kp, rec, src_row, Y, ncols, ldy, W, ldw, (int)n, var);    \
     } while (0)
     if (row_source == GPX_ROW_KERNEL) {
@@ -484,23 +526,24 @@ extern "C" int gpx_select_pivot(gpx_handle h, const double* recs, int nrec, int6
 }
 
 __global__ void __launch_bounds__(256) store_pivot_kernel(const double* __restrict__ rec, int n, double* U, int64_t ldu,
-                                                           int64_t* picks, double* scores) {
+                                                           int64_t* picks, double* scores, double* pivots) {
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
         if (U) U[(int64_t)i * ldu + n] = rec[GPX_PIVOT_HDR + i];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (U) U[(int64_t)n * ldu + n] = sqrt(rec[2]);
         if (picks) picks[n] = (int64_t)rec[1];
         if (scores) scores[n] = rec[0];
+        if (pivots) pivots[n] = rec[2];
     }
 }
 
 extern "C" int gpx_store_pivot(gpx_handle h, const double* rec, int64_t n, double* U, int64_t ldu, int64_t* picks,
-                               double* scores, void* stream) {
+                               double* scores, double* pivots, void* stream) {
     GPX_REQUIRE(h && rec && n >= 0, GPX_EINVAL, "bad arguments");
     unsigned grid = (unsigned)((n + 255) / 256);
     if (grid < 1) grid = 1;
     if (grid > 64) grid = 64;
-    store_pivot_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rec, (int)n, U, ldu, picks, scores);
+    store_pivot_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rec, (int)n, U, ldu, picks, scores, pivots);
     return gpx_check_launch("gpx_store_pivot");
 }
 

@@ -151,17 +151,10 @@ __global__ void __launch_bounds__(128) tri_solve_kernel(const double* __restrict
 }
 
 template <bool BACK>
-int launch_tri_solve(const double* Tm, int64_t ldt, int b, double* B, int64_t ldb, int64_t ncols, cudaStream_t st) {
-    static bool configured = false;
+int launch_tri_solve(gpx_handle h, const double* Tm, int64_t ldt, int b, double* B, int64_t ldb, int64_t ncols, cudaStream_t st) {
     const size_t smem = (size_t)NB * SLD * sizeof(double);
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tri_solve_kernel<BACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            gpx_set_error("tri_solve: shared memory opt-in failed: %s", cudaGetErrorString(e));
-            return (int)e;
-        }
-        configured = true;
-    }
+    int rc = gpx_ensure_smem(h, (const void*)tri_solve_kernel<BACK>, smem, "tri_solve");
+    if (rc) return rc;
     if (ncols <= 0 || b <= 0) return GPX_OK;
     tri_solve_kernel<BACK><<<(unsigned)((ncols + 127) / 128), 128, (size_t)b * SLD * sizeof(double), st>>>(Tm, ldt, b, B, ldb, ncols);
     return gpx_check_launch("tri_solve");
@@ -175,18 +168,16 @@ extern "C" int gpx_potrf(gpx_handle h, double* A, int64_t n, int64_t ld, int* in
     GPX_REQUIRE(h && info && n >= 0, GPX_EINVAL, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     set_int_kernel<<<1, 1, 0, st>>>(info, 0);
-    if (n == 0) return gpx_check_launch("gpx_potrf");
+    {
+        int rc = gpx_check_launch("gpx_potrf");
+        if (rc || n == 0) return rc;
+    }
     GPX_REQUIRE(A && ld >= n, GPX_EINVAL, "bad matrix");
     GPX_REQUIRE((ld % 2) == 0 && gpx_aligned16(A), GPX_EALIGN, "A must be 16-byte aligned with an even leading dimension");
-    static bool configured = false;
     const size_t smem = (size_t)NB * SLD * sizeof(double);
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            gpx_set_error("gpx_potrf: shared memory opt-in failed: %s", cudaGetErrorString(e));
-            return (int)e;
-        }
-        configured = true;
+    {
+        int rc = gpx_ensure_smem(h, (const void*)potrf_diag_kernel, smem, "gpx_potrf");
+        if (rc) return rc;
     }
     for (int64_t kb = 0; kb < n; kb += NB) {
         const int b = (int)(n - kb < NB ? n - kb : NB);
@@ -196,7 +187,7 @@ extern "C" int gpx_potrf(gpx_handle h, double* A, int64_t n, int64_t ld, int* in
         const int64_t rest = n - kb - b;
         if (rest > 0) {
             double* A12 = A + kb * ld + kb + b;
-            rc = launch_tri_solve<false>(A + kb * ld + kb, ld, b, A12, ld, rest, st);
+            rc = launch_tri_solve<false>(h, A + kb * ld + kb, ld, b, A12, ld, rest, st);
             if (rc) return rc;
             rc = gpx_dgemm_tn_sub(h, A12, ld, A12, ld, A + (kb + b) * ld + kb + b, ld, rest, rest, b, 1, stream);
             if (rc) return rc;
@@ -205,24 +196,24 @@ extern "C" int gpx_potrf(gpx_handle h, double* A, int64_t n, int64_t ld, int* in
     return GPX_OK;
 }
 
-extern "C" int gpx_trsm_gram(gpx_handle h, const double* U, int64_t n, int64_t ldu, const double* Da_rows,
-                             const double* Da_scal, int64_t ldd, const double* Y, const double* Yb_rows, const double* Yb_scal,
-                             int64_t ny, int64_t ldy, double* W, int64_t ldw, double* var_out, void* stream) {
+extern "C" int gpx_trsm_gram(gpx_handle h, int prologue, const double* U, int64_t n, int64_t ldu, const double* Da_rows,
+                             int64_t ldd, const double* Y, const double* Yb_rows, int64_t ny, int64_t ldy, double* W,
+                             int64_t ldw, double* var_out, void* stream) {
     GPX_NEED_KERNEL(h);
     GPX_REQUIRE(n >= 0 && ny >= 0, GPX_EINVAL, "negative size");
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     if (ny == 0) return GPX_OK;
     if (n > 0) {
-        GPX_REQUIRE(U && Da_rows && Da_scal && Yb_rows && Yb_scal && W, GPX_EINVAL, "NULL pointer");
+        GPX_REQUIRE(U && Da_rows && Yb_rows && W, GPX_EINVAL, "NULL pointer");
         GPX_REQUIRE(ldd == ldu, GPX_EINVAL, "the prepared design side must share the leading dimension of U");
         for (int64_t kb = 0; kb < n; kb += NB) {
             const int b = (int)(n - kb < NB ? n - kb : NB);
             // block row:  W[kb:kb+b, :] = K(D[kb:kb+b], Y) - U[0:kb, kb:kb+b]^T W[0:kb, :]
-            rc = gpx_launch_core_store(h, U + kb, ldu, Da_rows + kb, Da_scal + kb, b, W, ldw, Yb_rows, Yb_scal, ny, kb,
-                                       W + kb * ldw, ldw, st);
+            rc = gpx_launch_core_store(h, prologue, U + kb, ldu, Da_rows + kb, b, W, ldw, Yb_rows, ny, kb, W + kb * ldw, ldw,
+                                       st);
             if (rc) return rc;
-            rc = launch_tri_solve<false>(U + kb * ldu + kb, ldu, b, W + kb * ldw, ldw, ny, st);
+            rc = launch_tri_solve<false>(h, U + kb * ldu + kb, ldu, b, W + kb * ldw, ldw, ny, st);
             if (rc) return rc;
         }
     }
@@ -248,7 +239,7 @@ static int trsm_forward(gpx_handle h, const double* U, int64_t n, int64_t ldu, d
             rc = gpx_dgemm_tn_sub(h, U + kb, ldu, B, ldb, B + kb * ldb, ldb, b, active, kb, 0, stream);
             if (rc) return rc;
         }
-        rc = launch_tri_solve<false>(U + kb * ldu + kb, ldu, b, B + kb * ldb, ldb, active, st);
+        rc = launch_tri_solve<false>(h, U + kb * ldu + kb, ldu, b, B + kb * ldb, ldb, active, st);
         if (rc) return rc;
     }
     return GPX_OK;
@@ -300,7 +291,7 @@ extern "C" int gpx_trsm_back(gpx_handle h, const double* Ut, int64_t n, int64_t 
                                   below, 0, stream);
             if (rc) return rc;
         }
-        rc = launch_tri_solve<true>(Ut + kb * ldu + kb, ldu, b, B + kb * ldb, ldb, ncols, st);
+        rc = launch_tri_solve<true>(h, Ut + kb * ldu + kb, ldu, b, B + kb * ldb, ldb, ncols, st);
         if (rc) return rc;
     }
     return GPX_OK;
@@ -363,7 +354,10 @@ extern "C" int gpx_chol_append(gpx_handle h, double* U, int64_t n, int64_t ld, c
     GPX_REQUIRE(knew || n == 0, GPX_EINVAL, "knew is NULL");
     const size_t smem = (size_t)n * sizeof(double);
     GPX_REQUIRE(smem <= 200 * 1024, GPX_ESIZE, "design size exceeds the shared-memory buffer (25600)");
-    if (smem > 48 * 1024) cudaFuncSetAttribute(chol_append_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (smem > 48 * 1024) {
+        int rc = gpx_ensure_smem(h, (const void*)chol_append_kernel, 200 * 1024, "gpx_chol_append");
+        if (rc) return rc;
+    }
     chol_append_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(U, (int)n, ld, knew, kpp, info);
     return gpx_check_launch("gpx_chol_append");
 }

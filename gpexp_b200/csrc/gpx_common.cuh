@@ -25,6 +25,12 @@ struct KParams {
     double c[GPX_MAX_DIM];    // MEHLER: 1 / (2 (1 - t_i^2))
 };
 
+#define GPX_SMEM_FUNCS 96
+
+struct KCenter {
+    double c[GPX_MAX_DIM];
+};
+
 struct gpx_context {
     int device;
     int sm_count;
@@ -36,12 +42,23 @@ struct gpx_context {
     unsigned int* red_counter;// last-block-done tickets (zero between calls)
     double* scal;             // a few device scalars (sum of varM ...)
     int64_t* iscal;
+    // centre subtracted from every coordinate by gpx_prep_side (stationary families only): keeps the expanded-form
+    // prologue k = f(alpha + beta + u.v) well conditioned for un-normalised inputs
+    double center[GPX_MAX_DIM];
+    // kernels already opted in to > 48 KB of dynamic shared memory ON THIS DEVICE (the attribute is per device)
+    const void* smem_ready[GPX_SMEM_FUNCS];
+    int n_smem_ready;
+    // optional NCCL communicator (gpx_comm_init); the library resolves NCCL at run time, it does not link it
+    void* nccl_comm;
+    int comm_rank, comm_size;
 };
 
 #define GPX_RED_SLOTS 2048
 
 void gpx_set_error(const char* fmt, ...);
 int gpx_check_launch(const char* what);
+// opt `func` in to `bytes` of dynamic shared memory once per handle (= per device)
+int gpx_ensure_smem(gpx_handle h, const void* func, size_t bytes, const char* name);
 
 #define GPX_REQUIRE(cond, code, msg)                 \
     do {                                             \
@@ -164,9 +181,12 @@ __device__ __forceinline__ double kexpand(double e, const KParams& kp) {
 // ---------------------------------------------------------------------------------------------
 // (value, index) ordering of np.argmax / np.argmin: better value wins, ties go to the lower index.
 // ---------------------------------------------------------------------------------------------
+// A NaN beats every number (np.argmax / np.argmin return the first NaN), so NaN scores surface instead of hiding.
 __device__ __forceinline__ bool gpx_better(double v, int64_t i, double bv, int64_t bi, bool minimize) {
     if (i < 0) return false;
     if (bi < 0) return true;
+    const bool vn = (v != v), bn = (bv != bv);
+    if (vn || bn) return vn && (!bn || i < bi);
     if (minimize ? (v < bv) : (v > bv)) return true;
     return (v == bv) && (i < bi);
 }
@@ -184,12 +204,12 @@ __device__ __forceinline__ void gpx_warp_argreduce(double& v, int64_t& i, bool m
 }
 
 // internal launchers shared between translation units
-int gpx_launch_core_ivar(gpx_handle h, const double* Wm, int64_t ldm, const double* Ma_rows, const double* Ma_scal,
-                         int64_t M, const double* Wc, int64_t ldc, const double* Cb_rows, const double* Cb_scal,
-                         int64_t C, int64_t n, double* partial, int64_t ldp, int* nsplit_out, cudaStream_t st);
-int gpx_launch_core_store(gpx_handle h, const double* A, int64_t lda, const double* Ap, const double* As,
-                          int64_t I, const double* B, int64_t ldb, const double* Bp, const double* Bs, int64_t J,
-                          int64_t K, double* out, int64_t ldo, cudaStream_t st);
+int gpx_launch_core_ivar(gpx_handle h, int prologue, const double* Wm, int64_t ldm, const double* Ma_rows, int64_t M,
+                         const double* Wc, int64_t ldc, const double* Cb_rows, int64_t C, int64_t n, double* partial,
+                         int64_t ldp, int* nsplit_out, cudaStream_t st);
+int gpx_launch_core_store(gpx_handle h, int prologue, const double* A, int64_t lda, const double* Ap, int64_t I,
+                          const double* B, int64_t ldb, const double* Bp, int64_t J, int64_t K, double* out, int64_t ldo,
+                          cudaStream_t st);
 int gpx_ivar_splits(gpx_handle h, int64_t M, int64_t C);
 int gpx_argreduce_impl(gpx_handle h, const double* v, const double* weights, const uint8_t* mask, int64_t n,
                        int minimize, double* best, int64_t* idx, cudaStream_t st);

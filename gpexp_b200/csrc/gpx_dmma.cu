@@ -2,21 +2,28 @@
 //
 //   T[i,j] = sum_k A[k*lda + i] * B[k*ldb + j]           both operands K-major (row k contiguous)
 //
-// with an optional *prologue* that evaluates the covariance k(x_i, y_j) on the tensor pipe as well
-// (expanded form  k = f(alpha_i + beta_j + sum_q u_q(i) v_q(j)),  q < 16 extra K rows), and three epilogues:
+// with an optional *prologue* that evaluates the covariance k(x_i, y_j) inside the same kernel, and three epilogues:
 //
 //   EPI_IVAR   r[j] += sum_i (k(i,j) - T[i,j])^2          K5: IVAR scoring, experimentalDesign.py:105-117 restated
 //   EPI_STORE  out[i,j] = k(i,j) - T[i,j]                  K1+K3: block row of the left-looking TRSM
 //   EPI_SUB    C[i,j]  -= T[i,j]                           K2: Cholesky trailing update / materialised TRSM / MI set-up
 //
+// Prologue forms (GPX_PRO_*):
+//   EXPANDED   k = f(e), e = sum_q u_q(i) v_q(j) over the d+2 rows of two *prepared sides* (gpx_prep_side): the d
+//              scaled coordinates plus the rows (alpha_i, 1) x (1, beta_j), so that the whole exponent -- including the
+//              |x|^2 and |y|^2 terms -- comes out of ONE extra DMMA chunk on the tensor pipe.  Cancellation error
+//              ~ eps * max|alpha|: the host only selects it when that is below 1e-11 (after centring), else
+//   DIFF       k = f(sum_q a_q (x_q - y_q)^2) from the raw coordinates staged in shared memory (difference form, the
+//              arithmetic of kernels.py:121-122 itself): no cancellation, d FP64 operations more per pair.
+//
 // sm_100a has no f64 kind in tcgen05, so the FP64 tensor path is warp-level mma.sync.m8n8k4 (SASS DMMA.8x8x4)
 // fed from shared memory.  Two kernels share the fragment layout:
 //
 //   ivar_ws_kernel     THE hot kernel (EPI_IVAR on fully padded operands): 128x128 CTA tile, 8 warps of 32x64,
-//                      operand chunks by TMA bulk copies completing on mbarriers (3-stage ring of 32-row chunks),
-//                      no CTA barrier in the main loop, table-driven exp prologue, butterfly column reduction.
-//   dmma_core_kernel   the generic predicated kernel (cp.async ring + __syncthreads, zero-filled edges) used for
-//                      EPI_STORE / EPI_SUB and as the fallback for unpadded IVAR operands.
+//                      operand chunks by TMA bulk copies completing on mbarriers, no CTA barrier in the main loop,
+//                      table-driven exp prologue, butterfly column reduction.
+//   dmma_core_kernel   the generic predicated kernel (cp.async ring + __syncthreads, zero-filled edges, 64x128 tile,
+//                      2 CTAs per SM) used for EPI_STORE / EPI_SUB and for unpadded IVAR operands.
 //
 // Rows are padded to 132 doubles and the fragment <-> matrix index map is permuted so that every thread reads
 // 2 adjacent doubles per conflict-free LDS.128:
@@ -28,14 +35,8 @@
 
 #include "gpx_common.cuh"
 
-#ifndef GPX_DEFAULT_WM
-#define GPX_DEFAULT_WM 2
-#endif
-#ifndef GPX_DEFAULT_IVAR_TN
-#define GPX_DEFAULT_IVAR_TN 8
-#endif
-#ifndef GPX_DEFAULT_IVAR_GROUP
-#define GPX_DEFAULT_IVAR_GROUP 1
+#ifndef GPX_DEFAULT_IVAR_RING
+#define GPX_DEFAULT_IVAR_RING 0
 #endif
 
 namespace {
@@ -55,11 +56,12 @@ constexpr int BK = 16;
 constexpr int STAGES = 4;
 
 enum { EPI_IVAR = 0, EPI_STORE = 1, EPI_SUB = 2 };
+enum { PRO_NONE = 0, PRO_EXPANDED = GPX_PRO_EXPANDED, PRO_DIFF = GPX_PRO_DIFF };
 
-// WM = warps along i.  WM=4: 256 threads, 128x128 tile, 1 CTA/SM.  WM=2: 128 threads, 64x128 tile, 2 CTAs/SM
-// (two independent CTAs de-phase the barriers and the exp prologue against each other's DMMA stream).
-template <int WM>
+// generic kernel geometry: 2 warps along i: 128 threads, 64x128 tile, 2 CTAs/SM (two independent CTAs de-phase the
+// barriers and the exp prologue against each other's DMMA stream)
 struct Cfg {
+    static constexpr int WM = 2;
     static constexpr int NT = WM * 64;
     static constexpr int BM = WM * 32;
     static constexpr int LDA = BM + 4;  // row strides = 4 (mod 16) doubles: conflict-free LDS.128 fragment loads
@@ -69,7 +71,7 @@ struct Cfg {
     static constexpr int PIECES = BK * (BM + BN) / 2;
     static constexpr int PER_THREAD = PIECES / NT;
     static constexpr int A_ITERS = PIECES_A / NT;
-    static constexpr int SMEM_DOUBLES = STAGES * STAGE + 2 * BM + BN + WM * BN;
+    static constexpr int SMEM_DOUBLES = STAGES * STAGE + WM * BN + 256;
     static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES * sizeof(double);
     static_assert(PIECES % NT == 0 && PIECES_A % NT == 0, "loader mapping");
 };
@@ -77,15 +79,13 @@ struct Cfg {
 struct CoreArgs {
     const double* A;   // K x I (main operand)
     const double* B;   // K x J
-    const double* Ap;  // prologue rows (GPX_KROWS x lda), same column space as A
-    const double* Bp;  // prologue rows (GPX_KROWS x ldb)
-    const double* As;  // alpha[I]
-    const double* Bs;  // beta[J]
+    const double* Ap;  // prologue rows, same column space as A: prepared side (EXPANDED) or raw coordinates (DIFF)
+    const double* Bp;  // prologue rows of the B side
     double* out;       // IVAR: partial sums [split][ldo] ; STORE / SUB: row-major I x J
     int64_t lda, ldb, ldo;
     int64_t I, J;
     int K;
-    int dpad;          // prologue K extent, multiple of 4
+    int prows;         // prologue rows to stage: EXPANDED roundup(d+2, 4), DIFF d
     int tiles_per_cta; // IVAR: i-tiles each CTA walks
     int upper_only;    // SUB: skip tiles below the diagonal ; ivar_ws_kernel: candidate tiles per wave group
     int ldo_splits;    // ivar_ws_kernel: number of M-splits
@@ -131,15 +131,102 @@ __device__ __forceinline__ void mma_tile(double (&acc)[4][8][2], const double (&
         for (int u = 0; u < 8; ++u) dmma(acc[t][u][0], acc[t][u][1], af[t], bf[u]);
 }
 
-template <int FAM, int EPI, bool PRO, int WM>
-__global__ void __launch_bounds__(WM * 64, WM == 4 ? 1 : 2)
+// Difference-form covariance of the warp's 32x64 accumulator block from coordinates staged in shared memory:
+// sa / sb point at row 0 of the staged A / B coordinates, offset to this thread's first i / j (see the index map).
+// On exit acc = -k(i,j).
+template <int FAM, int LDA_, int LDB_>
+__device__ __forceinline__ void diff_prologue(double (&acc)[4][8][2], const KParams& kp, const double* __restrict__ sa,
+                                              const double* __restrict__ sb, const double* __restrict__ tab) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
+#pragma unroll 1
+    for (int q = 0; q < kp.d; ++q) {
+        double x[4], y[8][2];
+#pragma unroll
+        for (int t2 = 0; t2 < 2; ++t2) {
+            const double2 v = *reinterpret_cast<const double2*>(sa + q * LDA_ + t2 * 16);
+            x[t2 * 2] = v.x;
+            x[t2 * 2 + 1] = v.y;
+        }
+#pragma unroll
+        for (int u2 = 0; u2 < 4; ++u2)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double2 v = *reinterpret_cast<const double2*>(sb + q * LDB_ + u2 * 16 + e * 2);
+                y[u2 * 2][e] = v.x;
+                y[u2 * 2 + 1][e] = v.y;
+            }
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) kacc_dim<FAM>(acc[t][u][e], kp, q, x[t], y[u][e]);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) acc[t][u][e] = -kfinish_tab<FAM>(acc[t][u][e], kp, tab);
+}
+
+// squares of the warp's accumulator block summed over its 32 rows: butterfly reduce-scatter over the 8 lanes that
+// share q4; lane g4 ends up owning columns u = g4, e = 0, 1
+__device__ __forceinline__ void column_squares(const double (&acc)[4][8][2], bool full, int64_t i_first, int64_t I, int lane,
+                                               double (&rs)[2]) {
+    const int g4 = lane >> 2;
+    double p[8][2];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) p[u][0] = p[u][1] = 0.0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int64_t i = i_first + (t >> 1) * 16 + g4 * 2 + (t & 1);
+        const bool ok = full || (i < I);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double v = ok ? acc[t][u][e] : 0.0;
+                p[u][e] = fma(v, v, p[u][e]);
+            }
+    }
+    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+    double h[4][2], q[2][2];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const double keep = b4 ? p[u + 4][e] : p[u][e];
+            const double send = b4 ? p[u][e] : p[u + 4][e];
+            h[u][e] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const double keep = b3 ? h[u + 2][e] : h[u][e];
+            const double send = b3 ? h[u][e] : h[u + 2][e];
+            q[u][e] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const double keep = b2 ? q[1][e] : q[0][e];
+        const double send = b2 ? q[0][e] : q[1][e];
+        rs[e] += keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+}
+
+template <int FAM, int EPI, int PRO>
+__global__ void __launch_bounds__(Cfg::NT, 2)
     dmma_core_kernel(const __grid_constant__ CoreArgs a, const __grid_constant__ KParams kp) {
-    using C = Cfg<WM>;
-    constexpr int BM = C::BM, NT = C::NT, LDA = C::LDA, LDB = C::LDB;
+    using C = Cfg;
+    constexpr int WM = C::WM, BM = C::BM, NT = C::NT, LDA = C::LDA, LDB = C::LDB;
     extern __shared__ __align__(16) double smem[];
-    double* s_alpha = smem + STAGES * C::STAGE;  // [2][BM], by tile parity
-    double* s_beta = s_alpha + 2 * BM;
-    double* s_red = s_beta + BN;
+    double* s_red = smem + STAGES * C::STAGE;
+    double* s_tab = s_red + WM * BN;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -161,8 +248,12 @@ __global__ void __launch_bounds__(WM * 64, WM == 4 ? 1 : 2)
     }
     const int ntiles = it_end > it_begin ? (int)(it_end - it_begin) : 0;
     const int kch = (a.K + BK - 1) / BK;
-    const int T = (PRO ? 1 : 0) + kch;  // chunks per tile
+    const int T = (PRO != PRO_NONE ? 1 : 0) + kch;  // chunks per tile
     const int G = ntiles * T;
+
+    if (PRO != PRO_NONE) {
+        for (int i = tid; i < 256; i += NT) s_tab[i] = kp.signal * gpx_exp2_tab[i];
+    }
 
     // ---- chunk loader (cp.async ring, 3 chunks in flight) ------------------------------------------
     int is_g = 0, is_tl = 0, is_ch = 0;
@@ -171,12 +262,12 @@ __global__ void __launch_bounds__(WM * 64, WM == 4 ? 1 : 2)
             const int64_t i0 = (it_begin + is_tl) * BM;
             const double *srcA, *srcB;
             int krows;
-            if (PRO && is_ch == 0) {
+            if (PRO != PRO_NONE && is_ch == 0) {
                 srcA = a.Ap;
                 srcB = a.Bp;
-                krows = a.dpad;
+                krows = a.prows;
             } else {
-                const int kc = is_ch - (PRO ? 1 : 0);
+                const int kc = is_ch - (PRO != PRO_NONE ? 1 : 0);
                 srcA = a.A + (int64_t)kc * BK * a.lda;
                 srcB = a.B + (int64_t)kc * BK * a.ldb;
                 krows = a.K - kc * BK;
@@ -216,10 +307,6 @@ __global__ void __launch_bounds__(WM * 64, WM == 4 ? 1 : 2)
     double rs[2] = {0.0, 0.0};
     double af0[4], bf0[8], af1[4], bf1[8];
 
-    if (PRO) {
-        if (tid < BN) s_beta[tid] = (j0 + tid < a.J) ? a.Bs[j0 + tid] : 0.0;
-    }
-
     issue();
     issue();
     issue();
@@ -237,23 +324,29 @@ __global__ void __launch_bounds__(WM * 64, WM == 4 ? 1 : 2)
             for (int t = 0; t < 4; ++t)
 #pragma unroll
                 for (int u = 0; u < 8; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
-            if (PRO && tid < BM) s_alpha[(tl & 1) * BM + tid] = (i0 + tid < a.I) ? a.As[i0 + tid] : 0.0;
         }
         const double* pa = smem + (g % STAGES) * C::STAGE + fa;
         const double* pb = smem + (g % STAGES) * C::STAGE + BK * LDA + fb;
         int ksteps;
         bool next_full;
         {
-            const int kc = ch - (PRO ? 1 : 0);
-            if (PRO && ch == 0) {
-                ksteps = a.dpad >> 2;
+            const int kc = ch - (PRO != PRO_NONE ? 1 : 0);
+            if (PRO != PRO_NONE && ch == 0) {
+                ksteps = PRO == PRO_EXPANDED ? (a.prows >> 2) : 0;
             } else {
                 const int rem = a.K - kc * BK;
                 ksteps = rem >= BK ? 4 : ((rem + 3) >> 2);
             }
             next_full = (a.K - (kc + 1) * BK) >= BK;
         }
-        if (ksteps == 4) {
+        if (PRO == PRO_DIFF && ch == 0) {
+            // covariance in difference form from the staged raw coordinates
+            const double* sa = smem + (g % STAGES) * C::STAGE + wm * 32 + g4 * 2;
+            const double* sb = smem + (g % STAGES) * C::STAGE + BK * LDA + wn * 64 + q4 * 4;
+            diff_prologue<FAM, LDA, LDB>(acc, kp, sa, sb, s_tab);
+            midsync();
+            pre = false;
+        } else if (ksteps == 4) {
             // software-pipelined: fragments of k-step s+1 are fetched while the DMMAs of k-step s issue
             if (!pre) load_frags<LDA, LDB>(af0, bf0, pa, pb, 0);
             load_frags<LDA, LDB>(af1, bf1, pa, pb, 1);
@@ -263,7 +356,7 @@ __global__ void __launch_bounds__(WM * 64, WM == 4 ? 1 : 2)
             load_frags<LDA, LDB>(af1, bf1, pa, pb, 3);
             mma_tile(acc, af0, bf0);
             midsync();
-            const bool np = (ch + 1 < T) && !(PRO && ch == 0) && next_full;
+            const bool np = (ch + 1 < T) && !(PRO != PRO_NONE && ch == 0) && next_full;
             if (np) {
                 const double* na = smem + ((g + 1) % STAGES) * C::STAGE + fa;
                 const double* nb = smem + ((g + 1) % STAGES) * C::STAGE + BK * LDA + fb;
@@ -278,69 +371,25 @@ __global__ void __launch_bounds__(WM * 64, WM == 4 ? 1 : 2)
                 load_frags<LDA, LDB>(af0, bf0, pa, pb, ks);
                 mma_tile(acc, af0, bf0);
             }
+            if (ksteps == 0) midsync();
             pre = false;
         }
 
-        if (PRO && ch == 0) {
-            // covariance from the expanded form; accumulators become -k so that the main loop yields T - k
-            const double* sal = s_alpha + (tl & 1) * BM;
+        if (PRO == PRO_EXPANDED && ch == 0) {
+            // covariance from the expanded form (alpha, beta ride in the contraction); accumulators become -k so
+            // that the main loop yields T - k
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const double al = sal[wm * 32 + (t >> 1) * 16 + g4 * 2 + (t & 1)];
+            for (int t = 0; t < 4; ++t)
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const double be = s_beta[wn * 64 + (u >> 1) * 16 + (q4 * 2 + e) * 2 + (u & 1)];
-                        acc[t][u][e] = -kexpand<FAM>(acc[t][u][e] + al + be, kp);
-                    }
-            }
+                    for (int e = 0; e < 2; ++e) acc[t][u][e] = -kexpand_tab<FAM>(acc[t][u][e], kp, s_tab);
         }
 
         if (ch == T - 1) {
             // ---- tile epilogue ---------------------------------------------------------------------
             if (EPI == EPI_IVAR) {
-                const bool full = (i0 + BM <= a.I);
-                double p[8][2];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) p[u][0] = p[u][1] = 0.0;
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int64_t i = i0 + wm * 32 + (t >> 1) * 16 + g4 * 2 + (t & 1);
-                    const bool ok = full || (i < a.I);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const double v = ok ? acc[t][u][e] : 0.0;
-                            p[u][e] = fma(v, v, p[u][e]);
-                        }
-                }
-                // butterfly reduce-scatter over the 8 lanes that share q4: lane g4 ends up owning u = g4
-                const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
-                double h[4][2], q[2][2];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const double keep = b4 ? p[u + 4][e] : p[u][e];
-                        const double send = b4 ? p[u][e] : p[u + 4][e];
-                        h[u][e] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                    }
-#pragma unroll
-                for (int u = 0; u < 2; ++u)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const double keep = b3 ? h[u + 2][e] : h[u][e];
-                        const double send = b3 ? h[u][e] : h[u + 2][e];
-                        q[u][e] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                    }
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const double keep = b2 ? q[1][e] : q[0][e];
-                    const double send = b2 ? q[0][e] : q[1][e];
-                    rs[e] += keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                }
+                column_squares(acc, i0 + BM <= a.I, i0 + wm * 32, a.I, lane, rs);
             } else {
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
@@ -400,30 +449,50 @@ __global__ void __launch_bounds__(WM * 64, WM == 4 ? 1 : 2)
 
 // ---------------------------------------------------------------------------------------------
 // TMA + mbarrier IVAR contraction (the hot kernel): operand chunks arrive by TMA bulk copies
-// (cp.async.bulk -> UBLKCP) that complete on mbarriers; the eight warps do LDS.128 + DMMA and take turns
-// (warp g mod 8 for chunk g+WS_AHEAD) at issuing the bulk copies of a chunk -- a ninth, dedicated producer warp
-// would put three warps on one sub-partition and cap everybody at 168 registers.  No CTA-wide barrier in
-// the main loop, so warps drift apart and one warp's exp prologue / epilogue overlaps the other warp's
-// DMMA stream on the same sub-partition.
+// (cp.async.bulk -> UBLKCP) that complete on mbarriers; the eight warps do LDS.128 + DMMA and take turns at issuing
+// the bulk copies of a chunk -- a ninth, dedicated producer warp would put three warps on one sub-partition and cap
+// everybody at 168 registers.  No CTA-wide barrier in the main loop.
+//
+// Ring geometries (template RING):
+//   RingSync  32-row chunks, 3 stages, 1 chunk ahead; all 8 warps consume the same chunk at (nearly) the same time and
+//             rotate as producers.  Both warps of a sub-partition therefore reach the per-tile exp prologue together, and
+//             the FP64 pipe idles on its dependency latencies.
+//   RingLag   16-row chunks, 6 stages, 2 ahead; the warps form two groups -- A = warps 0-3 (columns 0-63) and
+//             B = warps 4-7 (columns 64-127), one of each per sub-partition -- and group B is held LAG chunks behind
+//             group A (it may start chunk c only once every A warp has started chunk c+LAG; one extra mbarrier per
+//             stage).  A's prologue / epilogue then overlaps B's DMMA stream on the same sub-partition and vice versa.
+//             Only group A produces.
 // Requires fully padded operands: lda, ldb multiples of 128 covering whole tiles (the engines guarantee it).
 // ---------------------------------------------------------------------------------------------
 constexpr int WS_BM = 128;
 constexpr int WS_LD = 132;
-// Ring geometry.  Measured on B200 (n = 2047 / n = 255, C = M = 100k): 16 rows x 6 stages, 3 chunks ahead: 34.18 TFLOP/s /
-// 165.5 ms; 32 rows x 3 stages, 1 ahead: 34.70 / 165.3 ms; 32 x 3 stages, 2 ahead: 23.7 / 240 ms -- the stage that is
-// refilled must have been released at least one whole chunk ago, or the producing warp blocks on the slowest consumer.
-#ifndef GPX_WS_BK
-#define GPX_WS_BK 32
-#define GPX_WS_STAGES 3
-#define GPX_WS_AHEAD 1
-#endif
-constexpr int WS_BK = GPX_WS_BK;           // K rows per chunk
-constexpr int WS_KSTEPS = WS_BK / 4;
-constexpr int WS_STAGE = WS_BK * 2 * WS_LD;  // doubles
-constexpr int WS_STAGES = GPX_WS_STAGES;   // ring depth
-constexpr int WS_AHEAD = GPX_WS_AHEAD;     // chunks in flight ahead of the consumers
-constexpr int WS_SMEM_DOUBLES = WS_STAGES * WS_STAGE + WS_STAGES * WS_BM + BN + 4 * BN + 2 * WS_STAGES + 256;
-constexpr size_t WS_SMEM_BYTES = (size_t)WS_SMEM_DOUBLES * sizeof(double);
+
+template <int BK_, int STAGES_, int AHEAD_, int LAG_>
+struct Ring {
+    static constexpr int RBK = BK_;                    // K rows per chunk
+    static constexpr int KSTEPS = BK_ / 4;
+    static constexpr int STAGE = BK_ * 2 * WS_LD;      // doubles
+    static constexpr int NSTAGES = STAGES_;            // ring depth
+    static constexpr int AHEAD = AHEAD_;               // chunks in flight ahead of the (leading) consumers
+    static constexpr int LAG = LAG_;                   // chunks group B trails group A by (0: one group)
+    static constexpr int SMEM_DOUBLES = STAGES_ * STAGE + 4 * BN + 3 * STAGES_ + 256;
+    static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES * sizeof(double);
+    static_assert(LAG_ == 0 || AHEAD_ + LAG_ <= STAGES_ - 2, "the refilled stage must have been released a chunk ago");
+    static_assert(AHEAD_ <= 4, "initial chunks are issued by the first warps of group A");
+};
+// Measured on B200, round 1 (n = 2047 / n = 255, C = M = 100k): 16 rows x 6 stages, 3 ahead: 34.18 TFLOP/s / 165.5 ms;
+// 32 rows x 3 stages, 1 ahead: 34.70 / 165.3 ms; 32 x 3, 2 ahead: 23.7 / 240 ms (the refilled stage must have been
+// released at least one whole chunk ago, or the producing warp blocks on the slowest consumer).
+using RingSync = Ring<32, 3, 1, 0>;
+using RingLag1 = Ring<16, 6, 2, 1>;
+using RingLag2 = Ring<16, 6, 2, 2>;
+
+// sub_ws_kernel keeps the round-1 ring
+constexpr int WS_BK = RingSync::RBK;
+constexpr int WS_KSTEPS = RingSync::KSTEPS;
+constexpr int WS_STAGE = RingSync::STAGE;
+constexpr int WS_STAGES = RingSync::NSTAGES;
+constexpr int WS_AHEAD = RingSync::AHEAD;
 
 __device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned int count) {
@@ -454,17 +523,7 @@ __device__ __forceinline__ void bulk_g2s(double* dst, const double* src, unsigne
                  : "memory");
 }
 
-// TN = B fragments per warp: 8 -> 8 warps of 32x64 (254 registers), 4 -> 16 warps of 32x32 (<= 128 registers, four
-// warps per sub-partition: the DMMA pipe only idles when all four are outside their DMMA stream at once).
-template <int TN>
-struct WsCfg {
-    static constexpr int WN = BN / (TN * 8);      // warps along the candidate dimension
-    static constexpr int NW = 4 * WN;             // warps per CTA
-    static constexpr int NT = NW * 32;
-};
-
-template <int TN>
-__device__ __forceinline__ void load_frags_ws(double (&af)[4], double (&bf)[TN], const double* pa, const double* pb, int ks) {
+__device__ __forceinline__ void load_frags_ws(double (&af)[4], double (&bf)[8], const double* pa, const double* pb, int ks) {
 #pragma unroll
     for (int t2 = 0; t2 < 2; ++t2) {
         const double2 v = *reinterpret_cast<const double2*>(pa + ks * 4 * WS_LD + t2 * 16);
@@ -472,24 +531,23 @@ __device__ __forceinline__ void load_frags_ws(double (&af)[4], double (&bf)[TN],
         af[t2 * 2 + 1] = v.y;
     }
 #pragma unroll
-    for (int u2 = 0; u2 < TN / 2; ++u2) {
+    for (int u2 = 0; u2 < 4; ++u2) {
         const double2 v = *reinterpret_cast<const double2*>(pb + ks * 4 * WS_LD + u2 * 16);
         bf[u2 * 2] = v.x;
         bf[u2 * 2 + 1] = v.y;
     }
 }
 
-template <int FAM, int TN>
-__global__ void __launch_bounds__(WsCfg<TN>::NT, 1)
-    ivar_ws_kernel(const __grid_constant__ CoreArgs a, const __grid_constant__ KParams kp) {
-    constexpr int BM = WS_BM, LD = WS_LD, NW = WsCfg<TN>::NW, NT = WsCfg<TN>::NT, WCOLS = TN * 8;
+template <int FAM, int PRO, class RING>
+__global__ void __launch_bounds__(256, 1) ivar_ws_kernel(const __grid_constant__ CoreArgs a, const __grid_constant__ KParams kp) {
+    constexpr int BM = WS_BM, LD = WS_LD, NW = 8;
+    constexpr int RBK = RING::RBK, NST = RING::NSTAGES, AHEAD = RING::AHEAD, LAG = RING::LAG;
     extern __shared__ __align__(16) double smem[];
-    double* s_alpha = smem + WS_STAGES * WS_STAGE;  // [WS_STAGES][BM], travels with the prologue chunk
-    double* s_beta = s_alpha + WS_STAGES * BM;
-    double* s_red = s_beta + BN;
+    double* s_red = smem + NST * RING::STAGE;
     uint64_t* full = reinterpret_cast<uint64_t*>(s_red + 4 * BN);
-    uint64_t* empty = full + WS_STAGES;
-    double* s_tab = reinterpret_cast<double*>(empty + WS_STAGES);  // signal * 2^(j/256)
+    uint64_t* empty = full + NST;
+    uint64_t* astart = empty + NST;                                  // RingLag: group A has started the chunk of this stage
+    double* s_tab = reinterpret_cast<double*>(astart + NST);         // signal * 2^(j/256)
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -511,19 +569,19 @@ __global__ void __launch_bounds__(WsCfg<TN>::NT, 1)
     int64_t it_end = it_begin + a.tiles_per_cta;
     if (it_end > itiles) it_end = itiles;
     const int ntiles = it_end > it_begin ? (int)(it_end - it_begin) : 0;
-    const int kch = (a.K + WS_BK - 1) / WS_BK;
+    const int kch = (a.K + RBK - 1) / RBK;
     const int T = 1 + kch;
     const int G = ntiles * T;
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < WS_STAGES; ++s) {
+        for (int s = 0; s < NST; ++s) {
             mbar_init(full + s, 1);
             mbar_init(empty + s, NW);
+            mbar_init(astart + s, 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if (tid < BN) s_beta[tid] = (j0 + tid < a.J) ? a.Bs[j0 + tid] : 0.0;
     if (tid < 256) s_tab[tid] = kp.signal * gpx_exp2_tab[tid];
     __syncthreads();
 
@@ -535,8 +593,8 @@ __global__ void __launch_bounds__(WsCfg<TN>::NT, 1)
     //      copies issue back to back from one lane (UBLKCP takes uniform registers) -----------------------
     auto produce = [&](int c) {
         if (c >= G) return;
-        const int s = c % WS_STAGES;
-        const unsigned int ph = (unsigned int)(c / WS_STAGES) & 1u;
+        const int s = c % NST;
+        const unsigned int ph = (unsigned int)(c / NST) & 1u;
         mbar_wait(empty + s, ph ^ 1u);
         const int ptl = c / T, pch = c - ptl * T;
         const int64_t i0 = (it_begin + ptl) * BM;
@@ -545,18 +603,18 @@ __global__ void __launch_bounds__(WsCfg<TN>::NT, 1)
         if (pch == 0) {
             srcA = a.Ap + i0;
             srcB = a.Bp + j0;
-            krows = a.dpad;
-            ksteps = a.dpad >> 2;
+            krows = a.prows;  // EXPANDED: a multiple of 4 (zero rows are part of the prepared side); DIFF: d, no DMMA
+            ksteps = PRO == PRO_EXPANDED ? (a.prows >> 2) : 0;
         } else {
             const int kc = pch - 1;
-            srcA = a.A + (int64_t)kc * WS_BK * a.lda + i0;
-            srcB = a.B + (int64_t)kc * WS_BK * a.ldb + j0;
-            const int rem = a.K - kc * WS_BK;
-            krows = rem < WS_BK ? rem : WS_BK;
-            ksteps = rem >= WS_BK ? WS_KSTEPS : ((rem + 3) >> 2);
+            srcA = a.A + (int64_t)kc * RBK * a.lda + i0;
+            srcB = a.B + (int64_t)kc * RBK * a.ldb + j0;
+            const int rem = a.K - kc * RBK;
+            krows = rem < RBK ? rem : RBK;
+            ksteps = rem >= RBK ? RING::KSTEPS : ((rem + 3) >> 2);
         }
-        double* stA = smem + s * WS_STAGE;
-        double* stB = stA + WS_BK * LD;
+        double* stA = smem + s * RING::STAGE;
+        double* stB = stA + RBK * LD;
         if (krows < ksteps * 4) {
             // K tail: rows the DMMAs will read but the operand does not have -> explicit zeros (lane -> column pair)
             for (int r = krows; r < ksteps * 4; ++r) {
@@ -569,142 +627,86 @@ __global__ void __launch_bounds__(WsCfg<TN>::NT, 1)
             __syncwarp();
         }
         if (lane == 0) {
-            const unsigned int bytes = (unsigned int)krows * (BM + BN) * 8u + (pch == 0 ? BM * 8u : 0u);
-            mbar_arrive_expect_tx(full + s, bytes);
+            mbar_arrive_expect_tx(full + s, (unsigned int)krows * (BM + BN) * 8u);
 #pragma unroll 4
             for (int r = 0; r < krows; ++r) {
                 bulk_g2s(stA + r * LD, srcA + (int64_t)r * a.lda, BM * 8u, full + s);
                 bulk_g2s(stB + r * LD, srcB + (int64_t)r * a.ldb, BN * 8u, full + s);
             }
-            if (pch == 0) bulk_g2s(s_alpha + s * BM, a.As + i0, BM * 8u, full + s);
         }
         __syncwarp();
     };
-    if (warp < WS_AHEAD) produce(warp);
+    if (LAG == 0) {
+        if (warp < AHEAD) produce(warp);
+    } else {
+        if (wn == 0 && wm < AHEAD) produce(wm);
+    }
 
     {
-        double acc[4][TN][2];
-        double af0[4], bf0[TN];
+        double acc[4][8][2];
+        double af0[4], bf0[8];
         const int fa = q4 * LD + wm * 32 + g4 * 2;
-        const int fb = WS_BK * LD + q4 * LD + wn * WCOLS + g4 * 2;
+        const int fb = RBK * LD + q4 * LD + wn * 64 + g4 * 2;
         int tl = 0, ch = 0;
         for (int g = 0; g < G; ++g) {
-            const int s = g % WS_STAGES;
-            const unsigned int ph = (unsigned int)(g / WS_STAGES) & 1u;
+            const int s = g % NST;
+            const unsigned int ph = (unsigned int)(g / NST) & 1u;
             const int64_t i0 = (it_begin + tl) * BM;
-            if (warp == (g & (NW - 1))) produce(g + WS_AHEAD);
-            if (ch == 0) {
+            if (LAG == 0) {
+                if (warp == (g & (NW - 1))) produce(g + AHEAD);
+            } else {
+                if (wn == 0 && wm == (g & 3)) produce(g + AHEAD);
+                // group B stays LAG chunks behind group A (not enforced over the last LAG chunks of the CTA)
+                if (wn == 1 && g + LAG < G) mbar_wait(astart + (g + LAG) % NST, (unsigned int)((g + LAG) / NST) & 1u);
+            }
+            if (ch == 0 && PRO != PRO_DIFF) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
 #pragma unroll
-                    for (int u = 0; u < TN; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
+                    for (int u = 0; u < 8; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
             }
             mbar_wait(full + s, ph);
-            const double* pa = smem + s * WS_STAGE + fa;
-            const double* pb = smem + s * WS_STAGE + fb;
-            int ksteps;
-            if (ch == 0) {
-                ksteps = a.dpad >> 2;
+            if (LAG > 0 && wn == 0) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(astart + s);
+            }
+            const double* pa = smem + s * RING::STAGE + fa;
+            const double* pb = smem + s * RING::STAGE + fb;
+            if (ch == 0 && PRO == PRO_DIFF) {
+                diff_prologue<FAM, LD, LD>(acc, kp, smem + s * RING::STAGE + wm * 32 + g4 * 2,
+                                           smem + s * RING::STAGE + RBK * LD + wn * 64 + q4 * 4, s_tab);
             } else {
-                const int rem = a.K - (ch - 1) * WS_BK;
-                ksteps = rem >= WS_BK ? WS_KSTEPS : ((rem + 3) >> 2);
-            }
-            // single-buffered fragments: the other warps of the sub-partition cover the LDS latency (double
-            // buffering measured identical: 34.44 vs 34.43 TFLOP/s at n = 4095)
+                int ksteps;
+                if (ch == 0) {
+                    ksteps = a.prows >> 2;
+                } else {
+                    const int rem = a.K - (ch - 1) * RBK;
+                    ksteps = rem >= RBK ? RING::KSTEPS : ((rem + 3) >> 2);
+                }
+                // single-buffered fragments: the other warp of the sub-partition covers the LDS latency (double
+                // buffering measured identical in round 1: 34.44 vs 34.43 TFLOP/s at n = 4095)
 #pragma unroll 1
-            for (int ks = 0; ks < ksteps; ++ks) {
-                load_frags_ws<TN>(af0, bf0, pa, pb, ks);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    load_frags_ws(af0, bf0, pa, pb, ks);
+                    mma_tile(acc, af0, bf0);
+                }
+                if (ch == 0) {
+                    // covariance from the expanded form (alpha, beta are two rows of the contraction); accumulators
+                    // become -k so that the main loop yields T - k
 #pragma unroll
-                for (int t = 0; t < 4; ++t)
+                    for (int t = 0; t < 4; ++t)
 #pragma unroll
-                    for (int u = 0; u < TN; ++u) dmma(acc[t][u][0], acc[t][u][1], af0[t], bf0[u]);
-            }
-            if (ch == 0) {
-                // covariance from the expanded form; accumulators become -k so that the main loop yields T - k
-                const double* sal = s_alpha + s * BM;
+                        for (int u = 0; u < 8; ++u)
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const double al = sal[wm * 32 + (t >> 1) * 16 + g4 * 2 + (t & 1)];
-#pragma unroll
-                    for (int u = 0; u < TN; ++u)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const double be = s_beta[wn * WCOLS + (u >> 1) * 16 + (q4 * 2 + e) * 2 + (u & 1)];
-                            acc[t][u][e] = -kexpand_tab<FAM>(acc[t][u][e] + al + be, kp, s_tab);
-                        }
+                            for (int e = 0; e < 2; ++e) acc[t][u][e] = -kexpand_tab<FAM>(acc[t][u][e], kp, s_tab);
                 }
             }
-            // this warp is done with stage s (all its LDS results have been consumed by issued DMMAs)
+            // this warp is done with stage s (all its LDS results have been consumed)
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + s);
 
             if (ch == T - 1) {
-                const bool fullt = (i0 + BM <= a.I);
-                double p[TN][2];
-#pragma unroll
-                for (int u = 0; u < TN; ++u) p[u][0] = p[u][1] = 0.0;
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int64_t i = i0 + wm * 32 + (t >> 1) * 16 + g4 * 2 + (t & 1);
-                    const bool ok = fullt || (i < a.I);
-#pragma unroll
-                    for (int u = 0; u < TN; ++u)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const double v = ok ? acc[t][u][e] : 0.0;
-                            p[u][e] = fma(v, v, p[u][e]);
-                        }
-                }
-                // butterfly reduce-scatter over the 8 lanes that share q4
-                const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
-                if (TN == 8) {
-                    // lane g4 ends up owning u = g4 (both e)
-                    double h[4][2], q[2][2];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const double keep = b4 ? p[(u + 4) % TN][e] : p[u][e];
-                            const double send = b4 ? p[u][e] : p[(u + 4) % TN][e];
-                            h[u][e] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                        }
-#pragma unroll
-                    for (int u = 0; u < 2; ++u)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const double keep = b3 ? h[u + 2][e] : h[u][e];
-                            const double send = b3 ? h[u][e] : h[u + 2][e];
-                            q[u][e] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                        }
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const double keep = b2 ? q[1][e] : q[0][e];
-                        const double send = b2 ? q[0][e] : q[1][e];
-                        rs[e] += keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                    }
-                } else {
-                    // TN == 4: lane g4 ends up owning u = g4 >> 1, e = g4 & 1 (one value)
-                    double h[2][2], q[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const double keep = b4 ? p[(u + 2) % TN][e] : p[u][e];
-                            const double send = b4 ? p[u][e] : p[(u + 2) % TN][e];
-                            h[u][e] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                        }
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const double keep = b3 ? h[1][e] : h[0][e];
-                        const double send = b3 ? h[0][e] : h[1][e];
-                        q[e] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                    }
-                    {
-                        const double keep = b2 ? q[1] : q[0];
-                        const double send = b2 ? q[0] : q[1];
-                        rs[0] += keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                    }
-                }
+                column_squares(acc, i0 + BM <= a.I, i0 + wm * 32, a.I, lane, rs);
                 ch = 0;
                 ++tl;
             } else {
@@ -714,13 +716,8 @@ __global__ void __launch_bounds__(WsCfg<TN>::NT, 1)
     }
 
     __syncthreads();
-    if (TN == 8) {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) s_red[wm * BN + wn * WCOLS + (g4 >> 1) * 16 + (q4 * 2 + e) * 2 + (g4 & 1)] = rs[e];
-    } else {
-        const int u = g4 >> 1, e = g4 & 1;
-        s_red[wm * BN + wn * WCOLS + (u >> 1) * 16 + (q4 * 2 + e) * 2 + (u & 1)] = rs[0];
-    }
+    for (int e = 0; e < 2; ++e) s_red[wm * BN + wn * 64 + (g4 >> 1) * 16 + (q4 * 2 + e) * 2 + (g4 & 1)] = rs[e];
     __syncthreads();
     if (tid < BN && j0 + tid < a.J) {
         const double r = ((s_red[tid] + s_red[BN + tid]) + s_red[2 * BN + tid]) + s_red[3 * BN + tid];
@@ -728,18 +725,10 @@ __global__ void __launch_bounds__(WsCfg<TN>::NT, 1)
     }
 }
 
-bool ivar_use_tma() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("GPX_IVAR_TMA");
-        v = (e && e[0] == '0') ? 0 : 1;
-    }
-    return v == 1;
-}
 // ---------------------------------------------------------------------------------------------
 // TMA + mbarrier variant of the plain update  C[i,j] -= sum_k A[k,i] B[k,j]  for callers that GUARANTEE fully padded
 // operands (every 128-wide tile of A and B readable and finite; the distributed MI set-up does).  Same ring, fragment
-// layout and rotating producer as ivar_ws_kernel, one 128x128 tile per CTA, no prologue.
+// layout and rotating producer as ivar_ws_kernel<RingSync>, one 128x128 tile per CTA, no prologue.
 // ---------------------------------------------------------------------------------------------
 constexpr int SUBWS_SMEM_DOUBLES = WS_STAGES * WS_STAGE + 2 * WS_STAGES;
 constexpr size_t SUBWS_SMEM_BYTES = (size_t)SUBWS_SMEM_DOUBLES * sizeof(double);
@@ -823,11 +812,8 @@ __global__ void __launch_bounds__(256, 1) sub_ws_kernel(const __grid_constant__ 
         const int ksteps = rem >= WS_BK ? WS_KSTEPS : ((rem + 3) >> 2);
 #pragma unroll 1
         for (int ks = 0; ks < ksteps; ++ks) {
-            load_frags_ws<8>(af0, bf0, pa, pb, ks);
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-#pragma unroll
-                for (int u = 0; u < 8; ++u) dmma(acc[t][u][0], acc[t][u][1], af0[t], bf0[u]);
+            load_frags_ws(af0, bf0, pa, pb, ks);
+            mma_tile(acc, af0, bf0);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
@@ -857,70 +843,42 @@ __global__ void __launch_bounds__(256, 1) sub_ws_kernel(const __grid_constant__ 
     }
 }
 
-int ivar_tn() {
-    static int v = 0;
-    if (v == 0) {
-        const char* e = getenv("GPX_IVAR_TN");
-        v = (e && e[0] == '8') ? 8 : ((e && e[0] == '4') ? 4 : GPX_DEFAULT_IVAR_TN);
+// which ring the hot kernel runs on: 0 = RingSync, 1 = RingLag1, 2 = RingLag2.  GPX_IVAR_RING overrides (A/B runs).
+int ivar_ring() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GPX_IVAR_RING");
+        v = (e && e[0] >= '0' && e[0] <= '2') ? (e[0] - '0') : GPX_DEFAULT_IVAR_RING;
     }
     return v;
 }
 
-template <int FAM, int TN>
-int launch_ivar_ws_tn(const CoreArgs& a, const KParams& kp, dim3 grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(ivar_ws_kernel<FAM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES);
-        if (e != cudaSuccess) {
-            gpx_set_error("ivar_ws: cannot opt in to %zu bytes of shared memory: %s", WS_SMEM_BYTES, cudaGetErrorString(e));
-            return (int)e;
-        }
-        configured = true;
-    }
-    ivar_ws_kernel<FAM, TN><<<grid, WsCfg<TN>::NT, WS_SMEM_BYTES, st>>>(a, kp);
+template <int FAM, int PRO, class RING>
+int launch_ivar_ws_ring(gpx_handle h, const CoreArgs& a, dim3 grid, cudaStream_t st) {
+    int rc = gpx_ensure_smem(h, (const void*)ivar_ws_kernel<FAM, PRO, RING>, RING::SMEM_BYTES, "ivar_ws");
+    if (rc) return rc;
+    ivar_ws_kernel<FAM, PRO, RING><<<grid, 256, RING::SMEM_BYTES, st>>>(a, h->kp);
     return gpx_check_launch("ivar_ws");
 }
-template <int FAM>
-int launch_ivar_ws(const CoreArgs& a, const KParams& kp, dim3 grid, cudaStream_t st) {
-    return ivar_tn() == 4 ? launch_ivar_ws_tn<FAM, 4>(a, kp, grid, st) : launch_ivar_ws_tn<FAM, 8>(a, kp, grid, st);
+
+template <int FAM, int PRO>
+int launch_ivar_ws(gpx_handle h, const CoreArgs& a, dim3 grid, cudaStream_t st) {
+    // the lagged rings stage 16-row chunks: every prologue fits (EXPANDED <= 16 rows, DIFF <= 16 coordinates)
+    switch (ivar_ring()) {
+        case 1: return launch_ivar_ws_ring<FAM, PRO, RingLag1>(h, a, grid, st);
+        case 2: return launch_ivar_ws_ring<FAM, PRO, RingLag2>(h, a, grid, st);
+        default: return launch_ivar_ws_ring<FAM, PRO, RingSync>(h, a, grid, st);
+    }
 }
 
-// tile shape used by every launch: GPX_WM=2 (64x128, 2 CTAs/SM) or 4 (128x128, 1 CTA/SM)
-int core_wm() {
-    static int wm = 0;
-    if (wm == 0) {
-        const char* e = getenv("GPX_WM");
-        wm = (e && e[0] == '4') ? 4 : ((e && e[0] == '2') ? 2 : GPX_DEFAULT_WM);
-    }
-    return wm;
-}
-
-template <int FAM, int EPI, bool PRO, int WM>
-int launch_core_wm(const CoreArgs& a, const KParams& kp, dim3 grid, cudaStream_t st) {
-    using C = Cfg<WM>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(dmma_core_kernel<FAM, EPI, PRO, WM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)C::SMEM_BYTES);
-        if (e != cudaSuccess) {
-            gpx_set_error("dmma core: cannot opt in to %zu bytes of shared memory: %s", C::SMEM_BYTES, cudaGetErrorString(e));
-            return (int)e;
-        }
-        configured = true;
-    }
-    dmma_core_kernel<FAM, EPI, PRO, WM><<<grid, C::NT, C::SMEM_BYTES, st>>>(a, kp);
+template <int FAM, int EPI, int PRO>
+int launch_core(gpx_handle h, const CoreArgs& a, int64_t jt, int64_t it_or_splits, cudaStream_t st) {
+    dim3 grid((unsigned)jt, (unsigned)it_or_splits);
+    int rc = gpx_ensure_smem(h, (const void*)dmma_core_kernel<FAM, EPI, PRO>, Cfg::SMEM_BYTES, "dmma core");
+    if (rc) return rc;
+    dmma_core_kernel<FAM, EPI, PRO><<<grid, Cfg::NT, Cfg::SMEM_BYTES, st>>>(a, h->kp);
     return gpx_check_launch("dmma core");
 }
-
-template <int FAM, int EPI, bool PRO>
-int launch_core(const CoreArgs& a, const KParams& kp, int64_t jt, int64_t it_or_splits, cudaStream_t st) {
-    dim3 grid((unsigned)jt, (unsigned)it_or_splits);
-    if (core_wm() == 4) return launch_core_wm<FAM, EPI, PRO, 4>(a, kp, grid, st);
-    return launch_core_wm<FAM, EPI, PRO, 2>(a, kp, grid, st);
-}
-
-int core_bm() { return core_wm() * 32; }
-
 
 int check_operand(const double* p, int64_t ld, const char* name) {
     if (!gpx_aligned16(p) || (ld & 1)) {
@@ -928,6 +886,13 @@ int check_operand(const double* p, int64_t ld, const char* name) {
         return GPX_EALIGN;
     }
     return GPX_OK;
+}
+
+// rows of the prologue chunk for this handle's kernel, or < 0 if the form cannot be used
+int prologue_rows(gpx_handle h, int prologue) {
+    if (prologue == PRO_DIFF) return h->kp.d;
+    if (prologue == PRO_EXPANDED && h->kp.d + 2 <= GPX_KROWS) return (h->kp.d + 2 + 3) & ~3;
+    return -1;
 }
 
 }  // namespace
@@ -956,10 +921,12 @@ static int ivar_splits_for(gpx_handle h, int64_t M, int64_t C, int bm) {
 }
 int gpx_ivar_splits(gpx_handle, int64_t, int64_t) { return 32; }  // workspace bound: never more than 32 splits
 
-int gpx_launch_core_ivar(gpx_handle h, const double* Wm, int64_t ldm, const double* Ma_rows, const double* Ma_scal,
-                         int64_t M, const double* Wc, int64_t ldc, const double* Cb_rows, const double* Cb_scal,
-                         int64_t C, int64_t n, double* partial, int64_t ldp, int* nsplit_out, cudaStream_t st) {
+int gpx_launch_core_ivar(gpx_handle h, int prologue, const double* Wm, int64_t ldm, const double* Ma_rows, int64_t M,
+                         const double* Wc, int64_t ldc, const double* Cb_rows, int64_t C, int64_t n, double* partial,
+                         int64_t ldp, int* nsplit_out, cudaStream_t st) {
     int rc;
+    const int prows = prologue_rows(h, prologue);
+    GPX_REQUIRE(prows >= 0, GPX_ESIZE, "prologue must be GPX_PRO_DIFF, or GPX_PRO_EXPANDED with d <= GPX_KROWS - 2");
     if ((rc = check_operand(Ma_rows, ldm, "Ma_rows"))) return rc;
     if ((rc = check_operand(Cb_rows, ldc, "Cb_rows"))) return rc;
     if (n > 0) {
@@ -968,10 +935,9 @@ int gpx_launch_core_ivar(gpx_handle h, const double* Wm, int64_t ldm, const doub
     }
     // the TMA path reads whole 128-wide tiles: operands must be padded to full tiles (the engines do that);
     // anything else goes through the predicated cp.async core
-    const bool padded = (ldm % WS_BM) == 0 && (ldc % BN) == 0 && ldm >= (M + WS_BM - 1) / WS_BM * WS_BM &&
-                        ldc >= (C + BN - 1) / BN * BN;
-    const bool tma = ivar_use_tma() && padded;
-    const int bm = tma ? WS_BM : core_bm();
+    const bool tma = (ldm % WS_BM) == 0 && (ldc % BN) == 0 && ldm >= (M + WS_BM - 1) / WS_BM * WS_BM &&
+                     ldc >= (C + BN - 1) / BN * BN;
+    const int bm = tma ? WS_BM : Cfg::BM;
     const int splits = ivar_splits_for(h, M, C, bm);
     const int64_t itl = (M + bm - 1) / bm;
     CoreArgs a;
@@ -979,8 +945,6 @@ int gpx_launch_core_ivar(gpx_handle h, const double* Wm, int64_t ldm, const doub
     a.B = Wc;
     a.Ap = Ma_rows;
     a.Bp = Cb_rows;
-    a.As = Ma_scal;
-    a.Bs = Cb_scal;
     a.out = partial;
     a.lda = ldm;
     a.ldb = ldc;
@@ -988,36 +952,41 @@ int gpx_launch_core_ivar(gpx_handle h, const double* Wm, int64_t ldm, const doub
     a.I = M;
     a.J = C;
     a.K = (int)n;
-    a.dpad = (h->kp.d + 3) & ~3;
+    a.prows = prows;
     a.tiles_per_cta = (int)((itl + splits - 1) / splits);
     a.upper_only = 0;
     a.ldo_splits = 0;
     *nsplit_out = splits;
     if (tma) {
         const int64_t jt = (C + BN - 1) / BN;
-        static int gmul = 0;
-        if (gmul == 0) {
-            const char* e = getenv("GPX_IVAR_GROUP");
-            gmul = (e && e[0] >= '1' && e[0] <= '8') ? (e[0] - '0') : GPX_DEFAULT_IVAR_GROUP;
-        }
-        // one CTA per SM: a group is `gmul` waves of candidate tiles (their W_C tiles must stay L2-resident)
-        const int64_t gw = (int64_t)gmul * (h->sm_count > 0 ? h->sm_count : 148);
+        // one CTA per SM: a group is one wave of candidate tiles (their W_C tiles must stay L2-resident)
+        const int64_t gw = (int64_t)(h->sm_count > 0 ? h->sm_count : 148);
         const int64_t groups = (jt + gw - 1) / gw;
         a.upper_only = (int)gw;
         a.ldo_splits = splits;
         // every group gets gw*splits CTA slots; the short last group leaves some idle (they exit at once)
         dim3 grid((unsigned)(groups * gw * splits), 1u);
-        GPX_DISPATCH_FAMILY(h->kp.family, rc = (launch_ivar_ws<FAM>(a, h->kp, grid, st)));
+        if (prologue == PRO_DIFF) {
+            GPX_DISPATCH_FAMILY(h->kp.family, rc = (launch_ivar_ws<FAM, PRO_DIFF>(h, a, grid, st)));
+        } else {
+            GPX_DISPATCH_FAMILY(h->kp.family, rc = (launch_ivar_ws<FAM, PRO_EXPANDED>(h, a, grid, st)));
+        }
         return rc;
     }
-    GPX_DISPATCH_FAMILY(h->kp.family, rc = (launch_core<FAM, EPI_IVAR, true>(a, h->kp, (C + BN - 1) / BN, splits, st)));
+    if (prologue == PRO_DIFF) {
+        GPX_DISPATCH_FAMILY(h->kp.family, rc = (launch_core<FAM, EPI_IVAR, PRO_DIFF>(h, a, (C + BN - 1) / BN, splits, st)));
+    } else {
+        GPX_DISPATCH_FAMILY(h->kp.family, rc = (launch_core<FAM, EPI_IVAR, PRO_EXPANDED>(h, a, (C + BN - 1) / BN, splits, st)));
+    }
     return rc;
 }
 
-int gpx_launch_core_store(gpx_handle h, const double* A, int64_t lda, const double* Ap, const double* As, int64_t I,
-                          const double* B, int64_t ldb, const double* Bp, const double* Bs, int64_t J, int64_t K,
-                          double* out, int64_t ldo, cudaStream_t st) {
+int gpx_launch_core_store(gpx_handle h, int prologue, const double* A, int64_t lda, const double* Ap, int64_t I,
+                          const double* B, int64_t ldb, const double* Bp, int64_t J, int64_t K, double* out, int64_t ldo,
+                          cudaStream_t st) {
     int rc;
+    const int prows = prologue_rows(h, prologue);
+    GPX_REQUIRE(prows >= 0, GPX_ESIZE, "prologue must be GPX_PRO_DIFF, or GPX_PRO_EXPANDED with d <= GPX_KROWS - 2");
     if ((rc = check_operand(Ap, lda, "Ap"))) return rc;
     if ((rc = check_operand(Bp, ldb, "Bp"))) return rc;
     if ((rc = check_operand(out, ldo, "out"))) return rc;
@@ -1030,8 +999,6 @@ int gpx_launch_core_store(gpx_handle h, const double* A, int64_t lda, const doub
     a.B = B;
     a.Ap = Ap;
     a.Bp = Bp;
-    a.As = As;
-    a.Bs = Bs;
     a.out = out;
     a.lda = lda;
     a.ldb = ldb;
@@ -1039,12 +1006,16 @@ int gpx_launch_core_store(gpx_handle h, const double* A, int64_t lda, const doub
     a.I = I;
     a.J = J;
     a.K = (int)K;
-    a.dpad = (h->kp.d + 3) & ~3;
+    a.prows = prows;
     a.tiles_per_cta = 1;
     a.upper_only = 0;
     a.ldo_splits = 0;
-    GPX_DISPATCH_FAMILY(h->kp.family,
-                        rc = (launch_core<FAM, EPI_STORE, true>(a, h->kp, (J + BN - 1) / BN, (I + core_bm() - 1) / core_bm(), st)));
+    const int64_t jt = (J + BN - 1) / BN, it = (I + Cfg::BM - 1) / Cfg::BM;
+    if (prologue == PRO_DIFF) {
+        GPX_DISPATCH_FAMILY(h->kp.family, rc = (launch_core<FAM, EPI_STORE, PRO_DIFF>(h, a, jt, it, st)));
+    } else {
+        GPX_DISPATCH_FAMILY(h->kp.family, rc = (launch_core<FAM, EPI_STORE, PRO_EXPANDED>(h, a, jt, it, st)));
+    }
     return rc;
 }
 
@@ -1062,7 +1033,7 @@ extern "C" int gpx_dgemm_tn_sub(gpx_handle h, const double* A, int64_t lda, cons
     CoreArgs a;
     a.A = A;
     a.B = B;
-    a.Ap = a.Bp = a.As = a.Bs = nullptr;
+    a.Ap = a.Bp = nullptr;
     a.out = C;
     a.lda = lda;
     a.ldb = ldb;
@@ -1070,12 +1041,11 @@ extern "C" int gpx_dgemm_tn_sub(gpx_handle h, const double* A, int64_t lda, cons
     a.I = I;
     a.J = J;
     a.K = (int)K;
-    a.dpad = 0;
+    a.prows = 0;
     a.tiles_per_cta = 1;
     a.upper_only = upper_only;
     a.ldo_splits = 0;
-    KParams kp = h->kp;
-    return launch_core<GPX_SE, EPI_SUB, false>(a, kp, (J + BN - 1) / BN, (I + core_bm() - 1) / core_bm(), (cudaStream_t)stream);
+    return launch_core<GPX_SE, EPI_SUB, PRO_NONE>(h, a, (J + BN - 1) / BN, (I + Cfg::BM - 1) / Cfg::BM, (cudaStream_t)stream);
 }
 
 // Same update for operands the CALLER guarantees to be fully padded (every 128-wide tile of A's I columns and B's J
@@ -1093,15 +1063,10 @@ extern "C" int gpx_dgemm_tn_sub_padded(gpx_handle h, const double* A, int64_t ld
     if ((rc = check_operand(C, ldc, "C"))) return rc;
     GPX_REQUIRE(lda >= (I + WS_BM - 1) / WS_BM * WS_BM && ldb >= (J + BN - 1) / BN * BN, GPX_EALIGN,
                 "padded variant needs leading dimensions that cover whole 128-wide tiles");
-    static const bool use_tma = []() {
-        const char* e = getenv("GPX_SUB_TMA");
-        return !(e && e[0] == '0');
-    }();
-    if (!use_tma) return gpx_dgemm_tn_sub(h, A, lda, B, ldb, C, ldc, I, J, K, upper_only, stream);
     CoreArgs a;
     a.A = A;
     a.B = B;
-    a.Ap = a.Bp = a.As = a.Bs = nullptr;
+    a.Ap = a.Bp = nullptr;
     a.out = C;
     a.lda = lda;
     a.ldb = ldb;
@@ -1109,39 +1074,105 @@ extern "C" int gpx_dgemm_tn_sub_padded(gpx_handle h, const double* A, int64_t ld
     a.I = I;
     a.J = J;
     a.K = (int)K;
-    a.dpad = 0;
+    a.prows = 0;
     a.tiles_per_cta = 1;
     a.upper_only = upper_only;
     a.ldo_splits = 0;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(sub_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SUBWS_SMEM_BYTES);
-        if (e != cudaSuccess) {
-            gpx_set_error("sub_ws: cannot opt in to %zu bytes of shared memory: %s", SUBWS_SMEM_BYTES, cudaGetErrorString(e));
-            return (int)e;
-        }
-        configured = true;
-    }
+    if ((rc = gpx_ensure_smem(h, (const void*)sub_ws_kernel, SUBWS_SMEM_BYTES, "sub_ws"))) return rc;
     dim3 grid((unsigned)((J + BN - 1) / BN), (unsigned)((I + WS_BM - 1) / WS_BM));
     sub_ws_kernel<<<grid, 256, SUBWS_SMEM_BYTES, (cudaStream_t)stream>>>(a);
     return gpx_check_launch("gpx_dgemm_tn_sub_padded");
 }
 
 // ---------------------------------------------------------------------------------------------
-// K5 + K7: IVAR scores of every candidate and their arg-min
+// K5 + K7: IVAR scores of every candidate and their arg-min.  The finalisation (sum the M-splits, apply the
+// pinv null-direction rule, |base - reduction|) and the first level of the arg-min share one kernel; the last block
+// to finish reduces the per-block winners (np.argmin order: lowest index wins ties).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ivar_finalize_kernel(const double* __restrict__ partial, int nsplit, int64_t ldp,
-                                                             const double* __restrict__ varC, const double* __restrict__ sumVarM,
-                                                             int64_t M, int64_t C, double noise, double zero_tol,
-                                                             double* __restrict__ score) {
-    const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (c >= C) return;
-    double r = 0.0;
-    for (int s = 0; s < nsplit; ++s) r += partial[(int64_t)s * ldp + c];
+__global__ void __launch_bounds__(256) ivar_finalize_argmin_kernel(const double* __restrict__ partial, int nsplit, int64_t ldp,
+                                                                    const double* __restrict__ varC,
+                                                                    const double* __restrict__ sumVarM, int64_t M, int64_t C,
+                                                                    double noise, double zero_tol,
+                                                                    const uint8_t* __restrict__ mask, double* __restrict__ score,
+                                                                    double* red_val, int64_t* red_idx, unsigned int* counter,
+                                                                    double* best, int64_t* idx) {
+    __shared__ double sv[8];
+    __shared__ int64_t si[8];
+    __shared__ bool last;
     const double base = sumVarM[0] / (double)M;            // (1/nMC) sum varMC   experimentalDesign.py:109
-    const double den = varC[c] + noise;
-    const double red = (den <= zero_tol) ? 0.0 : (r / den) / (double)M;
-    score[c] = fabs(base - red);                           // np.abs(cost)        experimentalDesign.py:117
+    double bv = 0.0;
+    int64_t bi = -1;
+    for (int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x; c < C; c += (int64_t)gridDim.x * 256) {
+        double r = 0.0;
+        for (int s = 0; s < nsplit; ++s) r += partial[(int64_t)s * ldp + c];
+        const double den = varC[c] + noise;
+        const double red = (den <= zero_tol) ? 0.0 : (r / den) / (double)M;
+        const double sc = fabs(base - red);                // np.abs(cost)        experimentalDesign.py:117
+        score[c] = sc;
+        if (!(mask && mask[c]) && gpx_better(sc, c, bv, bi, true)) {
+            bv = sc;
+            bi = c;
+        }
+    }
+    gpx_warp_argreduce(bv, bi, true);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        sv[warp] = bv;
+        si[warp] = bi;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        bv = lane < 8 ? sv[lane] : 0.0;
+        bi = lane < 8 ? si[lane] : -1;
+        gpx_warp_argreduce(bv, bi, true);
+        if (lane == 0) {
+            red_val[blockIdx.x] = bv;
+            red_idx[blockIdx.x] = bi;
+            __threadfence();
+            last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    bv = 0.0;
+    bi = -1;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += 256) {
+        const double ov = __ldcg(red_val + b);
+        const int64_t oi = __ldcg(red_idx + b);
+        if (gpx_better(ov, oi, bv, bi, true)) {
+            bv = ov;
+            bi = oi;
+        }
+    }
+    gpx_warp_argreduce(bv, bi, true);
+    if (lane == 0) {
+        sv[warp] = bv;
+        si[warp] = bi;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        bv = lane < 8 ? sv[lane] : 0.0;
+        bi = lane < 8 ? si[lane] : -1;
+        gpx_warp_argreduce(bv, bi, true);
+        if (lane == 0) {
+            best[0] = bv;
+            idx[0] = bi;
+            *counter = 0u;
+        }
+    }
+}
+
+static int ivar_finalize_argmin(gpx_handle h, const double* partial, int nsplit, int64_t ldp, const double* varC, int64_t M,
+                                int64_t C, double noise, double zero_tol, const uint8_t* mask, double* score_out, double* best,
+                                int64_t* idx, cudaStream_t st) {
+    int64_t blocks = (C + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    // slots [0, 1024) and ticket 0 of the handle scratch, like gpx_argreduce (never concurrent on one handle)
+    ivar_finalize_argmin_kernel<<<(unsigned)blocks, 256, 0, st>>>(partial, nsplit, ldp, varC, h->scal, M, C, noise, zero_tol,
+                                                                 mask, score_out, h->red_val, h->red_idx, h->red_counter, best,
+                                                                 idx);
+    return gpx_check_launch("gpx_score_ivar finalize");
 }
 
 extern "C" int64_t gpx_score_ivar_workspace(gpx_handle h, int64_t M, int64_t C) {
@@ -1150,28 +1181,22 @@ extern "C" int64_t gpx_score_ivar_workspace(gpx_handle h, int64_t M, int64_t C) 
     return (int64_t)gpx_ivar_splits(h, M, C) * ldp;
 }
 
-extern "C" int gpx_score_ivar(gpx_handle h, const double* Wm, int64_t ldm, const double* varM, const double* Ma_rows,
-                              const double* Ma_scal, int64_t M, const double* Wc, int64_t ldc, const double* varC,
-                              const double* Cb_rows, const double* Cb_scal, int64_t C, int64_t n, double noise,
-                              double zero_tol, const uint8_t* mask, double* workspace, double* score_out, double* best,
-                              int64_t* idx, void* stream) {
+extern "C" int gpx_score_ivar(gpx_handle h, int prologue, const double* Wm, int64_t ldm, const double* varM,
+                              const double* Ma_rows, int64_t M, const double* Wc, int64_t ldc, const double* varC,
+                              const double* Cb_rows, int64_t C, int64_t n, double noise, double zero_tol, const uint8_t* mask,
+                              double* workspace, double* score_out, double* best, int64_t* idx, void* stream) {
     GPX_NEED_KERNEL(h);
     GPX_REQUIRE(M >= 1 && C >= 1 && n >= 0, GPX_EINVAL, "bad sizes");
-    GPX_REQUIRE(varM && Ma_rows && Ma_scal && varC && Cb_rows && Cb_scal && workspace && score_out && best && idx,
-                GPX_EINVAL, "NULL pointer");
+    GPX_REQUIRE(varM && Ma_rows && varC && Cb_rows && workspace && score_out && best && idx, GPX_EINVAL, "NULL pointer");
     GPX_REQUIRE(n == 0 || (Wm && Wc), GPX_EINVAL, "W is NULL");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = gpx_sum_impl(h, varM, M, h->scal, st);
     if (rc) return rc;
     const int64_t ldp = (C + 1) & ~(int64_t)1;
     int nsplit = 1;
-    rc = gpx_launch_core_ivar(h, Wm, ldm, Ma_rows, Ma_scal, M, Wc, ldc, Cb_rows, Cb_scal, C, n, workspace, ldp, &nsplit, st);
+    rc = gpx_launch_core_ivar(h, prologue, Wm, ldm, Ma_rows, M, Wc, ldc, Cb_rows, C, n, workspace, ldp, &nsplit, st);
     if (rc) return rc;
-    ivar_finalize_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(workspace, nsplit, ldp, varC, h->scal, M, C, noise,
-                                                                     zero_tol, score_out);
-    rc = gpx_check_launch("gpx_score_ivar finalize");
-    if (rc) return rc;
-    return gpx_argreduce_impl(h, score_out, nullptr, mask, C, 1, best, idx, st);
+    return ivar_finalize_argmin(h, workspace, nsplit, ldp, varC, M, C, noise, zero_tol, mask, score_out, best, idx, st);
 }
 
 // IVAR scores from per-segment column sums of squares (resident-covariance mode): same finalisation + arg-min
@@ -1183,22 +1208,17 @@ extern "C" int gpx_score_ivar_partials(gpx_handle h, const double* partial, int 
     cudaStream_t st = (cudaStream_t)stream;
     int rc = gpx_sum_impl(h, varM, M, h->scal, st);
     if (rc) return rc;
-    ivar_finalize_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(partial, nseg, ldp, varC, h->scal, M, C, noise, zero_tol,
-                                                                     score_out);
-    rc = gpx_check_launch("gpx_score_ivar_partials finalize");
-    if (rc) return rc;
-    return gpx_argreduce_impl(h, score_out, nullptr, mask, C, 1, best, idx, st);
+    return ivar_finalize_argmin(h, partial, nseg, ldp, varC, M, C, noise, zero_tol, mask, score_out, best, idx, st);
 }
 
 // cov[m,c] = k(m,c) - sum_{i<n} Wm[i,m] Wc[i,c] for a GIVEN design (DMMA contraction with the Gram prologue, stored)
-extern "C" int gpx_cov_from_factors(gpx_handle h, const double* Wm, int64_t ldm, const double* Ma_rows, const double* Ma_scal,
-                                    int64_t M, const double* Wc, int64_t ldc, const double* Cb_rows, const double* Cb_scal,
-                                    int64_t C, int64_t n, double* cov, int64_t ldcov, void* stream) {
+extern "C" int gpx_cov_from_factors(gpx_handle h, int prologue, const double* Wm, int64_t ldm, const double* Ma_rows, int64_t M,
+                                    const double* Wc, int64_t ldc, const double* Cb_rows, int64_t C, int64_t n, double* cov,
+                                    int64_t ldcov, void* stream) {
     GPX_NEED_KERNEL(h);
-    GPX_REQUIRE(M >= 1 && C >= 1 && n >= 0 && cov && Ma_rows && Ma_scal && Cb_rows && Cb_scal, GPX_EINVAL, "bad arguments");
+    GPX_REQUIRE(M >= 1 && C >= 1 && n >= 0 && cov && Ma_rows && Cb_rows, GPX_EINVAL, "bad arguments");
     GPX_REQUIRE((M + 63) / 64 <= 65535, GPX_ESIZE, "M too large for one launch");
-    return gpx_launch_core_store(h, Wm, ldm, Ma_rows, Ma_scal, M, Wc, ldc, Cb_rows, Cb_scal, C, n, cov, ldcov,
-                                 (cudaStream_t)stream);
+    return gpx_launch_core_store(h, prologue, Wm, ldm, Ma_rows, M, Wc, ldc, Cb_rows, C, n, cov, ldcov, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------

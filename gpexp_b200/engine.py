@@ -16,15 +16,26 @@ to the lowest global index) -- so every rank appends bit-identical rows.
 """
 from __future__ import annotations
 
+import ctypes as C
+import warnings
+
 import numpy as np
 import torch
 
 from . import _lib
-from ._lib import check, lib
-from .device import Device, PointSet, F64, ptr, roundup
+from ._lib import GpxError, check, lib
+from .device import Device, PointSet, F64, prologue_operands, ptr, roundup
 
 HDR = _lib.GPX_PIVOT_HDR
 ZERO_VAR_TOL = 1e-13
+# A greedy step whose pivot var_D(p) + noise falls below this fraction of the prior variance means
+# cond(K_DD + noise I) >~ 1e7: eps * cond exceeds the 1e-9 parity contract with the reference's pinv arithmetic
+# (demo.py:52-58 stress values).  The run continues; the step is reported.
+PIVOT_WARN_RATIO = 1e-7
+
+
+class GpxConditionWarning(RuntimeWarning):
+    """The design Gram matrix became too ill conditioned for the 1e-9 parity contract (or was jittered to factor)."""
 
 
 class Shard:
@@ -46,6 +57,23 @@ class Shard:
 
     def all_gather(self, out: torch.Tensor, inp: torch.Tensor):
         self.dist.all_gather_into_tensor(out, inp, group=self.group)
+
+    def native(self, dev: Device) -> bool:
+        """Give the device handle its own NCCL communicator (gpx_comm_init) so that the C-side greedy loops can run
+        the per-step exchange themselves.  The 128-byte id travels over torch.distributed once.  NCCL groups only."""
+        if self.world == 1 or self.dist.get_backend(self.group) != "nccl":
+            return False
+        if int(lib.gpx_comm_size(dev.h)) == self.world:
+            return True
+        buf = (C.c_char * _lib.GPX_COMM_ID_BYTES)()
+        if self.rank == 0:
+            check(lib.gpx_comm_unique_id(buf, _lib.GPX_COMM_ID_BYTES), "gpx_comm_unique_id")
+        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(dev.torch_device)
+        self.dist.broadcast(t, src=self.dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        raw = bytes(t.cpu().numpy().tobytes())
+        torch.cuda.current_stream(dev.torch_device).synchronize()
+        check(lib.gpx_comm_init(dev.h, raw, self.rank, self.world), "gpx_comm_init")
+        return True
 
 
 def prior_scale(family: int, params) -> float:
@@ -74,6 +102,7 @@ class _Pivoting:
         self.idx = dev.zeros(1, dtype=torch.int64)
         self.picks = dev.zeros(max(n_max, 1), dtype=torch.int64)
         self.pick_scores = dev.zeros(max(n_max, 1))
+        self.pick_pivots = dev.zeros(max(n_max, 1))
         if shard is not None and shard.world > 1:
             self.rec_all = dev.zeros(shard.world * self.reclen)
             self.rec_win = dev.zeros(self.reclen)
@@ -85,12 +114,10 @@ class _Pivoting:
         dev = self.dev
         check(lib.gpx_gather_pivot(dev.h, ptr(W), ld, self.n, ptr(var), ptr(X.X), X.ld, ptr(self.best), ptr(self.idx),
                                    self.index_offset, noise, ptr(self.rec), dev.stream), "gpx_gather_pivot")
-        dev.launches += 1
         if self.rec_all is not None:
             self.shard.all_gather(self.rec_all, self.rec)
             check(lib.gpx_select_pivot(dev.h, ptr(self.rec_all), self.shard.world, self.reclen, self.n,
                                        1 if minimize else 0, ptr(self.rec_win), dev.stream), "gpx_select_pivot")
-            dev.launches += 1
 
     def _force_local(self, global_index: int):
         """Make `global_index` the pivot of this step (seeds / given designs): owner rank points at it."""
@@ -103,11 +130,37 @@ class _Pivoting:
     def _record(self, U=None, ldu=0):
         dev = self.dev
         check(lib.gpx_store_pivot(dev.h, ptr(self.rec_win), self.n, ptr(U), ldu, ptr(self.picks), ptr(self.pick_scores),
-                                  dev.stream), "gpx_store_pivot")
-        dev.launches += 1
+                                  ptr(self.pick_pivots), dev.stream), "gpx_store_pivot")
 
     def indices(self) -> np.ndarray:
         return self.picks[: self.n].cpu().numpy()
+
+    def pivots(self) -> np.ndarray:
+        """var_D(p) + noise of every pick, in pick order."""
+        return self.pick_pivots[: self.n].cpu().numpy()
+
+    def ill_conditioned_from(self, scale: float):
+        """First step whose pivot fell below PIVOT_WARN_RATIO * scale (None if none did); warns once."""
+        piv = self.pivots()
+        bad = np.nonzero(~(piv > PIVOT_WARN_RATIO * scale))[0]
+        if bad.size == 0:
+            return None
+        step = int(bad[0])
+        warnings.warn(f"greedy design: pivot {piv[step]:.3e} at step {step} is below {PIVOT_WARN_RATIO:g} x the prior "
+                      f"variance: the design Gram matrix is too ill conditioned for 1e-9 agreement with a pinv-based "
+                      f"evaluation from this step on (add noise or shorten the design)", GpxConditionWarning, stacklevel=3)
+        return step
+
+    def _native_ready(self) -> bool:
+        """The C-side loop can run this engine: single rank, or an NCCL shard whose ranks all hold candidates."""
+        if self.shard is None or self.shard.world == 1:
+            return True
+        if getattr(self, "_native", None) is None:
+            ok = self.shard.native(self.dev) and self._local_count() > 0
+            flag = torch.tensor([1 if ok else 0], device=self.dev.torch_device)
+            self.shard.dist.all_reduce(flag, op=self.shard.dist.ReduceOp.MIN, group=self.shard.group)
+            self._native = bool(flag.item())
+        return self._native
 
 
 class GreedyVarEngine(_Pivoting):
@@ -123,7 +176,6 @@ class GreedyVarEngine(_Pivoting):
         self.W = dev.zeros(ncap, pool.ld)
         self.var = dev.zeros(pool.ld)
         check(lib.gpx_prior_diag(dev.h, ptr(pool.X), pool.n, pool.ld, ptr(self.var), dev.stream), "gpx_prior_diag")
-        dev.launches += 1
         self.weights = None if weights is None else dev.upload(np.asarray(weights, dtype=np.float64))
         self.score_trace = None
 
@@ -134,14 +186,12 @@ class GreedyVarEngine(_Pivoting):
         dev = self.dev
         check(lib.gpx_argreduce(dev.h, ptr(self.var), ptr(self.weights), None, self.pool.n, 0, ptr(self.best),
                                 ptr(self.idx), dev.stream), "gpx_argreduce")
-        dev.launches += 1
 
     def append(self):
         dev, pool = self.dev, self.pool
         self._gather(self.W, pool.ld, self.var, pool, self.noise, minimize=False)
         check(lib.gpx_append_row(dev.h, _lib.ROW_KERNEL, ptr(self.rec_win), None, ptr(pool.X), pool.n, pool.ld,
                                  ptr(self.W), pool.ld, self.n, ptr(self.var), dev.stream), "gpx_append_row")
-        dev.launches += 1
         self._record()
         self.n += 1
 
@@ -156,11 +206,34 @@ class GreedyVarEngine(_Pivoting):
         self.select()
         self.append()
 
-    def run(self, n_points: int, progress=None):
+    def _state(self):
+        st = _lib.VarState()
+        pool = self.pool
+        st.X, st.C, st.ld, st.W, st.var, st.weights = ptr(pool.X), pool.n, pool.ld, ptr(self.W), ptr(self.var), ptr(self.weights)
+        st.ncap, st.index_offset, st.noise = self.ncap, self.index_offset, self.noise
+        st.best, st.idx, st.rec = ptr(self.best), ptr(self.idx), ptr(self.rec)
+        st.rec_all = ptr(self.rec_all)
+        st.rec_win = ptr(self.rec_win) if self.rec_all is not None else None
+        st.picks, st.pick_scores, st.pick_pivots = ptr(self.picks), ptr(self.pick_scores), ptr(self.pick_pivots)
+        return st
+
+    def run(self, n_points: int, progress=None, chunk: int = 10):
+        """Grow the design to n_points.  Without a score trace the steps are issued by the C-side loop
+        (gpx_var_greedy_run) in chunks of `chunk`, between which `progress(n)` is called (the reference prints every
+        10 points, experimentalDesign.py:812-813)."""
+        if self.score_trace is not None or not self._native_ready():
+            while self.n < n_points:
+                if progress is not None:
+                    progress(self.n)
+                self.step()
+            return self.indices()
+        st = self._state()
         while self.n < n_points:
             if progress is not None:
                 progress(self.n)
-            self.step()
+            stop = min(n_points, (self.n // chunk + 1) * chunk) if progress is not None else n_points
+            check(lib.gpx_var_greedy_run(self.dev.h, C.byref(st), self.n, stop, self.dev.stream), "gpx_var_greedy_run")
+            self.n = stop
         return self.indices()
 
 
@@ -181,12 +254,29 @@ class DesignFactor:
             nug_vec = dev.upload(nugget.astype(np.float64).ravel())
         else:
             nug = float(nugget)
+        self.jitter = 0.0
         if n:
             check(lib.gpx_gram(dev.h, ptr(design.X), n, design.ld, ptr(design.X), n, design.ld, ptr(self.U), self.ldu, 1,
                                ptr(nug_vec), nug, dev.stream), "gpx_gram")
             self._cov = self.U.clone()
             check(lib.gpx_potrf(dev.h, ptr(self.U), n, self.ldu, ptr(self.info), dev.stream), "gpx_potrf")
-            dev.launches += 2 + 3 * ((n + 127) // 128)
+            bad = int(self.info.item())
+            if bad:
+                # The reference pseudo-inverts (np.linalg.pinv, gp.py:181) and so tolerates numerically singular Grams
+                # (noise 0 with duplicate or nearly dependent nodes); a Cholesky factor does not exist there.  Retry once
+                # with a jitter at the level of pinv's own cut-off region, loudly; fail if that is not enough.
+                scale = float(torch.diagonal(self._cov[:n, :n]).abs().max().item())
+                self.jitter = 1e-10 * scale
+                warnings.warn(f"Gram matrix is not numerically positive definite (pivot {bad - 1} of {n}); factoring "
+                              f"K + {self.jitter:.3e} I instead -- results near the null directions differ from a "
+                              f"pseudo-inverse", GpxConditionWarning, stacklevel=3)
+                self.U.copy_(self._cov)
+                self.U[:n, :n].diagonal().add_(self.jitter)
+                check(lib.gpx_potrf(dev.h, ptr(self.U), n, self.ldu, ptr(self.info), dev.stream), "gpx_potrf")
+                bad = int(self.info.item())
+                if bad:
+                    raise GpxError(f"Gram matrix is not positive definite even with jitter {self.jitter:.3e}: "
+                                   f"failing pivot {bad - 1} of {n}")
         else:
             self._cov = self.U.clone()
         self._Ut = None
@@ -203,7 +293,6 @@ class DesignFactor:
             self._Ut = dev.zeros(max(self.n, 1), self.ldu)
             check(lib.gpx_transpose(dev.h, ptr(self.U), self.n, self.n, self.ldu, ptr(self._Ut), self.ldu, dev.stream),
                   "gpx_transpose")
-            dev.launches += 1
         return self._Ut
 
     def solve_gram(self, X: PointSet, W=None, want_var=True):
@@ -212,12 +301,11 @@ class DesignFactor:
         if W is None:
             W = dev.zeros(max(self.n, 1), X.ld)
         var = dev.zeros(X.ld) if want_var else None
-        da_rows, da_scal = D.side(_lib.SIDE_A)
-        xb_rows, xb_scal = X.side(_lib.SIDE_B)
-        check(lib.gpx_trsm_gram(dev.h, ptr(self.U), self.n, self.ldu, ptr(da_rows), ptr(da_scal), D.ld, ptr(X.X),
-                                ptr(xb_rows), ptr(xb_scal), X.n, X.ld, ptr(W), X.ld, ptr(var), dev.stream),
-              "gpx_trsm_gram")
-        dev.launches += 2 * ((self.n + 127) // 128) + 2
+        if self.n:
+            dev.set_center(X.midrange())
+        mode, da_rows, xb_rows = prologue_operands(D, X) if self.n else (_lib.PRO_DIFF, D.X, X.X)
+        check(lib.gpx_trsm_gram(dev.h, mode, ptr(self.U), self.n, self.ldu, ptr(da_rows), D.ld, ptr(X.X), ptr(xb_rows), X.n,
+                                X.ld, ptr(W), X.ld, ptr(var), dev.stream), "gpx_trsm_gram")
         return W, var
 
     def solve_vector(self, y: np.ndarray) -> np.ndarray:
@@ -234,7 +322,6 @@ class DesignFactor:
         dev = self.dev
         out = dev.zeros(1)
         check(lib.gpx_logdet_chol(dev.h, ptr(self.U), self.n, self.ldu, ptr(out), dev.stream), "gpx_logdet_chol")
-        dev.launches += 1
         return float(out.item())
 
     def whitened_norm2(self, y: np.ndarray) -> float:
@@ -263,7 +350,6 @@ class DesignFactor:
         out = dev.zeros(max(n * d, 1), X.ld)
         check(lib.gpx_se_var_grad(dev.h, ptr(D.X), n, D.ld, ptr(X.X), X.n, X.ld, ptr(W), ptr(qneg), ptr(out), dev.stream),
               "gpx_se_var_grad")
-        dev.launches += 4 + 2 * ((n + 127) // 128)
         return out
 
     def precision(self) -> np.ndarray:
@@ -298,21 +384,20 @@ class GreedyIVAREngine(_Pivoting):
         self.U = dev.zeros(ncap, roundup(ncap))
         check(lib.gpx_prior_diag(dev.h, ptr(cand.X), cand.n, cand.ld, ptr(self.varC), dev.stream), "gpx_prior_diag")
         check(lib.gpx_prior_diag(dev.h, ptr(mc.X), mc.n, mc.ld, ptr(self.varM), dev.stream), "gpx_prior_diag")
-        dev.launches += 2
         ws = int(lib.gpx_score_ivar_workspace(dev.h, mc.n, cand.n))
         self.workspace = dev.zeros(max(ws, 1))
         self.scores = dev.zeros(cand.ld)
         self.score_trace = None
         self.cov = None
+        self.nseg = int(lib.gpx_cov_segments(mc.n))
+        self.ldp = (cand.n + 1) & ~1
+        self.zero_scale = float(zero_scale)
         if self.resident:
-            self.nseg = int(lib.gpx_cov_segments(mc.n))
-            self.ldp = (cand.n + 1) & ~1
             self.cov = dev.empty(mc.n, cand.ld)
             # cov_0 = K(mc, cand), then the column sums of squares for the first scoring
             check(lib.gpx_gram(dev.h, ptr(mc.X), mc.n, mc.ld, ptr(cand.X), cand.n, cand.ld, ptr(self.cov), cand.ld, 0, None,
                                0.0, dev.stream), "gpx_gram")
             self._cov_pass(None, None)
-            dev.launches += 2
 
     def _local_count(self):
         return self.cand.n
@@ -322,6 +407,12 @@ class GreedyIVAREngine(_Pivoting):
         check(lib.gpx_cov_update(dev.h, ptr(self.cov), cand.ld, mc.n, cand.n, ptr(a), ptr(b), ptr(self.workspace), self.ldp,
                                  dev.stream), "gpx_cov_update")
 
+    def prologue(self):
+        """(mode, rows of the integration points, rows of the candidates) for the contraction's covariance prologue.
+        The centre of the expanded form is the mid-range of the integration points."""
+        self.dev.set_center(self.mc.midrange())
+        return prologue_operands(self.mc, self.cand)
+
     def score(self, contraction: bool = False):
         """Score every candidate and arg-min.  contraction=True forces the DMMA contraction even in resident mode
         (cross-check of the two paths on the same state)."""
@@ -330,20 +421,16 @@ class GreedyIVAREngine(_Pivoting):
             check(lib.gpx_score_ivar_partials(dev.h, ptr(self.workspace), self.nseg, self.ldp, ptr(self.varM), mc.n,
                                               ptr(self.varC), cand.n, self.noise, self.zero_tol, None, ptr(self.scores),
                                               ptr(self.best), ptr(self.idx), dev.stream), "gpx_score_ivar_partials")
-            dev.launches += 3
             return
-        ma_rows, ma_scal = mc.side(_lib.SIDE_A)
-        cb_rows, cb_scal = cand.side(_lib.SIDE_B)
+        mode, ma_rows, cb_rows = self.prologue()
         ws = self.workspace
         if self.resident:  # keep the resident column sums intact: the contraction gets its own scratch
             if getattr(self, "_ws2", None) is None:
                 self._ws2 = dev.zeros(self.workspace.numel())
             ws = self._ws2
-        check(lib.gpx_score_ivar(dev.h, ptr(self.Wm), mc.ld, ptr(self.varM), ptr(ma_rows), ptr(ma_scal), mc.n,
-                                 ptr(self.Wc), cand.ld, ptr(self.varC), ptr(cb_rows), ptr(cb_scal), cand.n, self.n,
-                                 self.noise, self.zero_tol, None, ptr(ws), ptr(self.scores), ptr(self.best),
-                                 ptr(self.idx), dev.stream), "gpx_score_ivar")
-        dev.launches += 4
+        check(lib.gpx_score_ivar(dev.h, mode, ptr(self.Wm), mc.ld, ptr(self.varM), ptr(ma_rows), mc.n, ptr(self.Wc), cand.ld,
+                                 ptr(self.varC), ptr(cb_rows), cand.n, self.n, self.noise, self.zero_tol, None, ptr(ws),
+                                 ptr(self.scores), ptr(self.best), ptr(self.idx), dev.stream), "gpx_score_ivar")
 
     def append(self):
         dev, cand, mc = self.dev, self.cand, self.mc
@@ -352,12 +439,10 @@ class GreedyIVAREngine(_Pivoting):
                                  ptr(self.Wc), cand.ld, self.n, ptr(self.varC), dev.stream), "gpx_append_row")
         check(lib.gpx_append_row(dev.h, _lib.ROW_KERNEL, ptr(self.rec_win), None, ptr(mc.X), mc.n, mc.ld,
                                  ptr(self.Wm), mc.ld, self.n, ptr(self.varM), dev.stream), "gpx_append_row")
-        dev.launches += 2
         self._record(self.U, self.U.shape[1])
         if self.resident:
             # cov -= w_M[n] w_C[n]^T and the next step's column sums of squares, one pass over the resident matrix
             self._cov_pass(self.Wm[self.n], self.Wc[self.n])
-            dev.launches += 1
         self.n += 1
 
     def force(self, global_index: int):
@@ -401,13 +486,11 @@ class GreedyIVAREngine(_Pivoting):
         self.varM.copy_(vM)
         if self.resident:
             dev, cand, mc = self.dev, self.cand, self.mc
-            ma_rows, ma_scal = mc.side(_lib.SIDE_A)
-            cb_rows, cb_scal = cand.side(_lib.SIDE_B)
-            check(lib.gpx_cov_from_factors(dev.h, ptr(self.Wm), mc.ld, ptr(ma_rows), ptr(ma_scal), mc.n, ptr(self.Wc), cand.ld,
-                                           ptr(cb_rows), ptr(cb_scal), cand.n, self.n, ptr(self.cov), cand.ld, dev.stream),
+            mode, ma_rows, cb_rows = self.prologue()
+            check(lib.gpx_cov_from_factors(dev.h, mode, ptr(self.Wm), mc.ld, ptr(ma_rows), mc.n, ptr(self.Wc), cand.ld,
+                                           ptr(cb_rows), cand.n, self.n, ptr(self.cov), cand.ld, dev.stream),
                   "gpx_cov_from_factors")
             self._cov_pass(None, None)
-            dev.launches += 2
 
     def step(self):
         self.score()
@@ -415,11 +498,39 @@ class GreedyIVAREngine(_Pivoting):
             self.score_trace.append(self.scores[: self.cand.n].cpu().numpy().copy())
         self.append()
 
-    def run(self, n_points: int, progress=None):
+    def _state(self):
+        st = _lib.IvarState()
+        cand, mc = self.cand, self.mc
+        mode, ma_rows, cb_rows = (_lib.PRO_DIFF, mc.X, cand.X) if self.resident else self.prologue()
+        self._state_keep = (ma_rows, cb_rows)
+        st.Xm, st.M, st.ldm, st.Wm, st.varM, st.Ma_rows = ptr(mc.X), mc.n, mc.ld, ptr(self.Wm), ptr(self.varM), ptr(ma_rows)
+        st.Xc, st.C, st.ldc, st.Wc, st.varC, st.Cb_rows = ptr(cand.X), cand.n, cand.ld, ptr(self.Wc), ptr(self.varC), ptr(cb_rows)
+        st.ncap, st.index_offset, st.prologue, st.nseg = self.ncap, self.index_offset, mode, self.nseg
+        st.noise, st.zero_tol = self.noise, self.zero_tol
+        st.workspace, st.scores, st.best, st.idx = ptr(self.workspace), ptr(self.scores), ptr(self.best), ptr(self.idx)
+        st.rec, st.rec_all = ptr(self.rec), ptr(self.rec_all)
+        st.rec_win = ptr(self.rec_win) if self.rec_all is not None else None
+        st.U, st.ldu = ptr(self.U), self.U.shape[1]
+        st.picks, st.pick_scores, st.pick_pivots = ptr(self.picks), ptr(self.pick_scores), ptr(self.pick_pivots)
+        st.cov, st.ldcov, st.ldp = ptr(self.cov), cand.ld, self.ldp
+        return st
+
+    def run(self, n_points: int, progress=None, chunk: int = 10):
+        """Grow the design to n_points: the whole loop is issued by gpx_ivar_greedy_run (one C call, no host round trip
+        per step) unless per-step score vectors are being traced."""
+        if self.score_trace is not None or not self._native_ready():
+            while self.n < n_points:
+                if progress is not None:
+                    progress(self.n)
+                self.step()
+            return self.indices()
+        st = self._state()
         while self.n < n_points:
             if progress is not None:
                 progress(self.n)
-            self.step()
+            stop = min(n_points, (self.n // chunk + 1) * chunk) if progress is not None else n_points
+            check(lib.gpx_ivar_greedy_run(self.dev.h, C.byref(st), self.n, stop, self.dev.stream), "gpx_ivar_greedy_run")
+            self.n = stop
         return self.indices()
 
 
@@ -456,7 +567,6 @@ class GreedyMIEngine(_Pivoting):
         self.mask = dev.zeros(ld, dtype=torch.uint8)
         self.scores = dev.zeros(ld)
         self.score_trace = None
-        dev.launches += 8 + 6 * ((v + 127) // 128)
 
     def _local_count(self):
         return self.pool.n
@@ -475,7 +585,6 @@ class GreedyMIEngine(_Pivoting):
         check(lib.gpx_append_row(dev.h, _lib.ROW_MATRIX, ptr(self.rec2), ptr(self.pcol), None, v, ld, ptr(self.Us), ld, self.n,
                                  ptr(self.pd), dev.stream), "gpx_append_row")
         check(lib.gpx_set_mask(dev.h, ptr(self.mask), ptr(self.idx), 1, dev.stream), "gpx_set_mask")
-        dev.launches += 7
         self._record()
         self.n += 1
 
@@ -487,7 +596,6 @@ class GreedyMIEngine(_Pivoting):
         dev = self.dev
         check(lib.gpx_score_mi(dev.h, ptr(self.num), ptr(self.pd), self.noise, ptr(self.mask), self.pool.n, ptr(self.scores),
                                ptr(self.best), ptr(self.idx), dev.stream), "gpx_score_mi")
-        dev.launches += 2
 
     def step(self):
         self.score()
@@ -522,6 +630,10 @@ class ShardedMIEngine(_Pivoting):
     def __init__(self, dev: Device, pool_host: np.ndarray, n_max: int, noise: float, shard=None):
         import os
         self.BLK = int(os.environ.get("GPX_MI_BLK", self.BLK))
+        if self.BLK < 128 or self.BLK & (self.BLK - 1):
+            # column offsets handed to gpx_dgemm_tn_sub_padded must stay multiples of the 128-wide TMA tiles while the
+            # block size is halved for small pools
+            raise ValueError(f"GPX_MI_BLK must be a power of two >= 128, got {self.BLK}")
         import torch.distributed as dist
         self.dist = dist
         self.noise = float(noise)
@@ -595,10 +707,18 @@ class ShardedMIEngine(_Pivoting):
         self.info = bad
         self.Y = Y
         del A, panel
+        self._init_greedy(n_max)
+
+    def _init_greedy(self, n_max: int):
+        """(Re)start the greedy state on the factorisation already held: nothing chosen, denominators from diag(Y^T Y)."""
+        dev, ld, V = self.dev, self.ld, self.V
+        nloc = self.hi - self.lo
+        st = dev.stream
+        ncap = max(int(n_max), 1)
+        self._init_pivot(dev, ncap, n_max, self.shard, self.lo)
         self.pd = dev.zeros(ld)
         if nloc > 0:
-            check(lib.gpx_colsumsq(dev.h, ptr(Y), V, nloc, ld, None, ptr(self.pd), st), "gpx_colsumsq")
-        # ---- greedy state
+            check(lib.gpx_colsumsq(dev.h, ptr(self.Y), V, nloc, ld, None, ptr(self.pd), st), "gpx_colsumsq")
         self.W = dev.zeros(ncap, ld)
         self.num = dev.zeros(ld)
         check(lib.gpx_prior_diag(dev.h, ptr(self.pool.X), nloc, ld, ptr(self.num), st), "gpx_prior_diag")
@@ -612,6 +732,11 @@ class ShardedMIEngine(_Pivoting):
         self.scores = dev.zeros(ld)
         self.score_trace = None
 
+    def reset(self, n_max: int):
+        """Forget the chosen points but keep the O(|V|^3) factorisation (costFunctionGP_MI.evaluate is called once per
+        candidate with a growing `indexAdded`, experimentalDesign.py:776-777)."""
+        self._init_greedy(n_max)
+
     def _local_count(self):
         return self.hi - self.lo
 
@@ -624,7 +749,6 @@ class ShardedMIEngine(_Pivoting):
             return
         check(lib.gpx_score_mi(dev.h, ptr(self.num), ptr(self.pd), self.noise, ptr(self.mask), nloc, ptr(self.scores),
                                ptr(self.best), ptr(self.idx), dev.stream), "gpx_score_mi")
-        dev.launches += 2
 
     def take(self):
         dev, pool, ld, V = self.dev, self.pool, self.ld, self.V
@@ -649,7 +773,6 @@ class ShardedMIEngine(_Pivoting):
             check(lib.gpx_append_row(dev.h, _lib.ROW_MATRIX, ptr(bufU), ptr(self.pcol), None, nloc, ld, ptr(self.Us), ld,
                                      self.n, ptr(self.pd), st), "gpx_append_row")
             check(lib.gpx_set_mask(dev.h, ptr(self.mask), ptr(self.loc2), 1, st), "gpx_set_mask")
-        dev.launches += 9
         self._record()
         self.n += 1
 

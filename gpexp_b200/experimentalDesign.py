@@ -72,7 +72,6 @@ class costFunctionGP_IVAR(costFunctionBase):
         _, var = f.solve_gram(mc)
         total = f.dev.zeros(1)
         check(lib.gpx_sum(f.dev.h, ptr(var), mc.n, ptr(total), f.dev.stream), "gpx_sum")
-        f.dev.launches += 1
         cost = 1.0 / float(self.nMC) * float(total.item())
         return np.abs(cost)
 
@@ -93,7 +92,6 @@ class costFunctionGP_IVAR(costFunctionBase):
         out = f.dev.zeros(max(rows, 1))
         check(lib.gpx_rowsum(f.dev.h, ptr(full), rows, mc.n, mc.ld, 1.0 / float(self.nMC), ptr(out), f.dev.stream),
               "gpx_rowsum")
-        f.dev.launches += 1
         return out[:rows].cpu().numpy()
 
 
@@ -116,12 +114,16 @@ class costFunctionGP_MI(costFunctionBase):
                 self.mcPoints = space.sample((self.nMC, space.dimension))
         self.gaussianProcess.addNodesAndComputeCovariance(self.mcPoints)
         self._engine = None
+        self._eval_engine = None
+        self._eval_prefix = []
 
     def add_candidates(self, nCandidates, candidates):
         self.nMC = nCandidates
         self.mcPoints = copy.deepcopy(candidates)
         self.gaussianProcess.addNodesAndComputeCovariance(self.mcPoints)
         self._engine = None
+        self._eval_engine = None  # the cached factorisation belongs to the old pool
+        self._eval_prefix = []
 
     # the reference stores these at construction and never reads them again (:241-242)
     @property
@@ -143,12 +145,31 @@ class costFunctionGP_MI(costFunctionBase):
         return ShardedMIEngine(dev, self.mcPoints, n_max, float(noise))
 
     def evaluate(self, index, indexAdded):
-        """MI ratio of candidate `index` given the already chosen `indexAdded` (:252-285); shape (1,)."""
-        eng = self._new_engine(len(indexAdded) + 1)
-        for i in indexAdded:
-            eng.force(int(i))
-        eng.score()
-        return eng.scores[int(index): int(index) + 1].cpu().numpy()
+        """MI ratio of candidate `index` given the already chosen `indexAdded` (:252-285); shape (1,).
+
+        The reference pays two pseudo-inverses per call; here the O(|V|^3) factorisation of the pool is built once and
+        kept (until add_candidates or a change of kernel / noise), the chosen points are replayed only when
+        `indexAdded` stops extending the previous call's list, and the scores of ALL candidates for that list are
+        kept, so the reference's loop `for ind in options: evaluate(ind, indKeep)` costs one scoring pass per step."""
+        added = [int(i) for i in indexAdded]
+        gp = self.gaussianProcess
+        key = (gp.kernel._gpx_spec()[0], tuple(np.ravel(gp.kernel._gpx_spec()[2])), float(_nugget_arg(gp.noise)))
+        eng = self._eval_engine
+        if eng is None or self._eval_key != key:
+            eng = self._eval_engine = self._new_engine(max(64, 2 * (len(added) + 1)))
+            self._eval_key, self._eval_prefix, self._eval_scores = key, [], None
+        else:
+            gp.kernel._bind(eng.dev)
+        if added[: len(self._eval_prefix)] != self._eval_prefix or len(added) > eng.ncap:
+            eng.reset(max(64, 2 * (len(added) + 1)))
+            self._eval_prefix, self._eval_scores = [], None
+        if len(added) > len(self._eval_prefix) or self._eval_scores is None:
+            for i in added[len(self._eval_prefix):]:
+                eng.force(i)
+            self._eval_prefix = added
+            eng.score()
+            self._eval_scores = eng.scores[: eng.pool.n].cpu().numpy()
+        return self._eval_scores[int(index): int(index) + 1].copy()
 
 
 class ExperimentalDesign(object):
@@ -319,11 +340,14 @@ def performGreedyIVARExperimentalDesign(costFuncIVAR, candidates, nPoints, retur
             flag = torch.tensor([1 if resident else 0], device=dev.torch_device)
             shard.dist.all_reduce(flag, op=shard.dist.ReduceOp.MIN, group=shard.group)
             resident = bool(flag.item())
-    eng = GreedyIVAREngine(dev, cand, mc, nPoints, float(noise), prior_scale(fam, params), shard=shard, index_offset=lo,
-                           resident=bool(resident))
+    scale = prior_scale(fam, params)
+    eng = GreedyIVAREngine(dev, cand, mc, nPoints, float(noise), scale, shard=shard, index_offset=lo, resident=bool(resident))
     idx = eng.run(nPoints)
     costFuncIVAR.lastIndices = idx
     costFuncIVAR.lastScores = eng.pick_scores[: eng.n].cpu().numpy()
+    costFuncIVAR.lastPivots = eng.pivots()
+    # first step from which 1e-9 agreement with the reference's pinv arithmetic cannot be expected (None: whole design)
+    costFuncIVAR.illConditionedFrom = eng.ill_conditioned_from(scale)
     if returnIndices:
         return idx
     return candidates[idx, :]

@@ -176,14 +176,12 @@ class GP:
         Kx = dev.zeros(max(n, 1), X.ld)
         check(lib.gpx_gram(dev.h, ptr(f.design.X), n, f.design.ld, ptr(X.X), q, X.ld, ptr(Kx), X.ld, 0, None, 0.0,
                            dev.stream), "gpx_gram")
-        dev.launches += 1
         # mean[j] = sum_k coeff[k] Kx[k, j]  as  C -= (-coeff)^T Kx  on the DMMA routine
         neg = np.zeros((max(n, 1), 2))
         neg[:n, 0] = -np.asarray(self.coeff, dtype=np.float64)
         mean = dev.zeros(2, X.ld)
         check(lib.gpx_dgemm_tn_sub(dev.h, ptr(dev.upload(neg)), 2, ptr(Kx), X.ld, ptr(mean), X.ld, 1, q, n, 0, dev.stream),
               "gpx_dgemm_tn_sub")
-        dev.launches += 1
         out = mean[0, :q].cpu().numpy() + self.gpPriorMean(newpt)
         if compvar == 1:
             _, var = f.solve_gram(X)
@@ -196,7 +194,6 @@ class GP:
             # covar[i, j] = k(x_i, x_j) - W[:, i] . W[:, j]  (gp.py:147-152)
             check(lib.gpx_dgemm_tn_sub(dev.h, ptr(W), X.ld, ptr(W), X.ld, ptr(Kqq), X.ld, q, q, n, 0, dev.stream),
                   "gpx_dgemm_tn_sub")
-            dev.launches += 2
             return out, Kqq[:q, :q].cpu().numpy()
         else:
             return out

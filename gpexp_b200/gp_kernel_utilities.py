@@ -26,6 +26,5 @@ def calculateCovarianceMatrix(kernel, points, nugget=0.0):
     # row j of the reference is kernel.evaluate(points, points[j]) = k(x_i, x_j) over i
     check(lib.gpx_gram(dev.h, ptr(P.X), size_of_mat, ld, ptr(P.X), size_of_mat, ld, ptr(out), ld, 1, ptr(nug_vec),
                        0.0 if nug_vec is not None else float(nugget), dev.stream), "gpx_gram")
-    dev.launches += 1
     # gpx_gram writes out[i, j] = k(X[i], Y[j]); the reference's [j, i] = k(x_i, x_j) is its transpose
     return out[:size_of_mat, :size_of_mat].t().contiguous().cpu().numpy()

@@ -64,7 +64,6 @@ class Kernel(object):
         out = dev.zeros(max(n, 1))
         check(lib.gpx_kernel_pairwise(dev.h, ptr(a.X), n1, a.ld, ptr(b.X), n2, b.ld, ptr(out), dev.stream),
               "gpx_kernel_pairwise")
-        dev.launches += 1
         return out[:n].cpu().numpy()
 
 
@@ -116,7 +115,6 @@ class KernelSquaredExponential(Kernel):
         ld = max(n * d, 1)
         out = dev.zeros(1, ld)
         check(lib.gpx_se_dgram(dev.h, ptr(b.X), 1, b.ld, ptr(a.X), n, a.ld, ptr(out), ld, dev.stream), "gpx_se_dgram")
-        dev.launches += 1
         return out[0, : n * d].cpu().numpy().reshape(n, d)
 
 

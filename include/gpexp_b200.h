@@ -29,10 +29,11 @@
 extern "C" {
 #endif
 
-#define GPX_VERSION 100
+#define GPX_VERSION 200
 
 #define GPX_MAX_DIM 16 /* largest supported input dimension                              */
-#define GPX_KROWS 16   /* rows of a prepared side: GPX_MAX_DIM, zero padded                */
+#define GPX_KROWS 16   /* rows of a prepared side: d scaled coordinates + (alpha, 1) + (1, beta), zero padded;
+                          the expanded-form prologue therefore serves d <= 14, larger d use the difference form */
 
 /* kernel families (gpExp/kernels.py) */
 #define GPX_SE 0       /* KernelSquaredExponential, iso or ARD      kernels.py:100-123     */
@@ -45,6 +46,13 @@ extern "C" {
 #define GPX_EALIGN (-2)    /* pointer / leading dimension not 16-byte aligned                */
 #define GPX_ENOKERNEL (-3) /* gpx_set_kernel not called                                      */
 #define GPX_ESIZE (-4)     /* size exceeds a documented limit                                */
+#define GPX_ENOCOMM (-5)   /* collective requested but gpx_comm_init was not called / NCCL not found */
+
+/* covariance prologue of the tensor-core routines */
+#define GPX_PRO_EXPANDED 1 /* k = f(sum of products of two prepared sides): one extra DMMA chunk; *_rows arguments are
+                              gpx_prep_side outputs.  Cancellation error ~ eps * max|alpha|: see gpx_prep_side.        */
+#define GPX_PRO_DIFF 2     /* k = f(sum a (x-y)^2) from raw coordinates (the arithmetic of kernels.py:121-122 itself);
+                              *_rows arguments are the dimension-major coordinate arrays.  No cancellation.            */
 
 /* sides of a prepared point set for the tensor-core Gram prologue */
 #define GPX_SIDE_A 0 /* the "row" operand (integration points / design rows)                  */
@@ -58,6 +66,9 @@ typedef struct gpx_context* gpx_handle;
 
 int gpx_version(void);
 const char* gpx_last_error(void);
+/* kernels launched by this library since it was loaded (process-wide; bench.py reports the difference over its timed
+ * region as `gpu_launches`) */
+int64_t gpx_launch_count(void);
 
 /* One handle per device.  Allocates a small reduction scratch; nothing else. */
 int gpx_create(int device, gpx_handle* out);
@@ -96,20 +107,27 @@ int gpx_potrf(gpx_handle h, double* A, int64_t n, int64_t ld, int* info, void* s
 int gpx_chol_append(gpx_handle h, double* U, int64_t n, int64_t ld, const double* knew, double kpp, int* info,
                     void* stream);
 
-/* Prepared side of a point set for the tensor-core Gram prologue: k(x,y) = f(alpha(x)+beta(y)+sum_i u_i(x) v_i(y)).
- *     rows  : GPX_KROWS x ld, rows >= d zero ; scal : ld entries. */
-int gpx_prep_side(gpx_handle h, int side, const double* X, int64_t n, int64_t ldx, double* rows, double* scal,
-                  int64_t ld, void* stream);
+/* Centre subtracted from every coordinate by gpx_prep_side for the stationary families (SE, Matern: k depends on x - y
+ * only, kernels.py:121-122, :87-89); ignored for Mehler.  center_host: d doubles, or NULL for the origin.  Both sides
+ * of a contraction must be prepared under the same centre. */
+int gpx_set_center(gpx_handle h, const double* center_host);
+
+/* Prepared side of a point set for the GPX_PRO_EXPANDED prologue: k(x,y) = f(sum_r rowsA[r][i] * rowsB[r][j]) with
+ *     rows  : GPX_KROWS x ld = d scaled coordinates, then (alpha_i | 1) and (1 | beta_j) for side A | B, then zeros;
+ *     maxabs (nullable, device): max |alpha| resp. |beta| -- the expanded form loses eps * (max|alpha| + max|beta|) to
+ *     cancellation, so the caller switches to GPX_PRO_DIFF when that exceeds its tolerance (1e-11 in gpexp_b200). */
+int gpx_prep_side(gpx_handle h, int side, const double* X, int64_t n, int64_t ldx, double* rows, int64_t ld,
+                  double* maxabs, void* stream);
 
 /* K1+K3  W = U^-T K(D, Y) without materialising K(D,Y):  left-looking blocked TRSM whose block rows are
  *     produced by the DMMA contraction kernel with the Gram evaluated in its prologue.  Replaces
  *     np.dot(precision, kernelvals) at gp.py:253-255 / experimentalDesign.py:836-837.
- *     Da_* / Yb_* are prepared sides (GPX_SIDE_A of the design with leading dimension ldd == ldu,
- *     GPX_SIDE_B of the query points with leading dimension ldw).
+ *     Da_rows / Yb_rows: per `prologue`, prepared sides (GPX_SIDE_A of the design, GPX_SIDE_B of the query points) or
+ *     the raw coordinates; leading dimensions ldd == ldu and ldw.
  *     var_out (nullable): var[j] = k(y_j,y_j) - sum_i W[i,j]^2     (K4, a7 GP.evaluateVariance). */
-int gpx_trsm_gram(gpx_handle h, const double* U, int64_t n, int64_t ldu, const double* Da_rows,
-                  const double* Da_scal, int64_t ldd, const double* Y, const double* Yb_rows, const double* Yb_scal,
-                  int64_t ny, int64_t ldy, double* W, int64_t ldw, double* var_out, void* stream);
+int gpx_trsm_gram(gpx_handle h, int prologue, const double* U, int64_t n, int64_t ldu, const double* Da_rows, int64_t ldd,
+                  const double* Y, const double* Yb_rows, int64_t ny, int64_t ldy, double* W, int64_t ldw, double* var_out,
+                  void* stream);
 
 /* In-place B <- U^-T B for a materialised right-hand side (n x ncols). */
 int gpx_trsm(gpx_handle h, const double* U, int64_t n, int64_t ldu, double* B, int64_t ncols, int64_t ldb,
@@ -175,13 +193,12 @@ int64_t gpx_score_ivar_workspace(gpx_handle h, int64_t M, int64_t C);
  *         r[c]     = sum_m ( k(m,c) - sum_{i<n} Wm[i,m] Wc[i,c] )^2            FP64 DMMA contraction
  *         cost[c]  = | sum(varM)/M - (r[c] / (varC[c] + noise)) / M |           (reduction = 0 if the
  *                    denominator is numerically zero: the pinv null-direction rule)
- *     then arg-min with lowest-index tie-break into best/idx.
- *     Ma_* : GPX_SIDE_A prepared integration points (leading dimension ldm);
- *     Cb_* : GPX_SIDE_B prepared candidates (leading dimension ldc). */
-int gpx_score_ivar(gpx_handle h, const double* Wm, int64_t ldm, const double* varM, const double* Ma_rows,
-                   const double* Ma_scal, int64_t M, const double* Wc, int64_t ldc, const double* varC,
-                   const double* Cb_rows, const double* Cb_scal, int64_t C, int64_t n, double noise,
-                   double zero_tol, const uint8_t* mask, double* workspace, double* score_out, double* best,
+ *     then arg-min with lowest-index tie-break into best/idx (a NaN score wins, as in np.argmin).
+ *     Ma_rows : integration points, Cb_rows : candidates -- per `prologue` the prepared sides (GPX_SIDE_A / GPX_SIDE_B)
+ *     or the raw coordinates; leading dimensions ldm / ldc. */
+int gpx_score_ivar(gpx_handle h, int prologue, const double* Wm, int64_t ldm, const double* varM, const double* Ma_rows,
+                   int64_t M, const double* Wc, int64_t ldc, const double* varC, const double* Cb_rows, int64_t C, int64_t n,
+                   double noise, double zero_tol, const uint8_t* mask, double* workspace, double* score_out, double* best,
                    int64_t* idx, void* stream);
 
 /* ---- Resident posterior covariance: the HBM-bound alternative for greedy IVAR loops -----------
@@ -192,9 +209,9 @@ int gpx_cov_segments(int64_t M);
 int gpx_cov_update(gpx_handle h, double* cov, int64_t ldcov, int64_t M, int64_t C, const double* a, const double* b,
                    double* partial, int64_t ldp, void* stream);
 /* cov = K(mc, cand) - Wm^T Wc for a given design (DMMA contraction, Gram in the prologue); n = 0 gives K itself. */
-int gpx_cov_from_factors(gpx_handle h, const double* Wm, int64_t ldm, const double* Ma_rows, const double* Ma_scal, int64_t M,
-                         const double* Wc, int64_t ldc, const double* Cb_rows, const double* Cb_scal, int64_t C, int64_t n,
-                         double* cov, int64_t ldcov, void* stream);
+int gpx_cov_from_factors(gpx_handle h, int prologue, const double* Wm, int64_t ldm, const double* Ma_rows, int64_t M,
+                         const double* Wc, int64_t ldc, const double* Cb_rows, int64_t C, int64_t n, double* cov, int64_t ldcov,
+                         void* stream);
 /* IVAR costs + arg-min from the per-segment sums (same finalisation as gpx_score_ivar). */
 int gpx_score_ivar_partials(gpx_handle h, const double* partial, int nseg, int64_t ldp, const double* varM, int64_t M,
                             const double* varC, int64_t C, double noise, double zero_tol, const uint8_t* mask,
@@ -230,8 +247,87 @@ int gpx_colsumsq(gpx_handle h, const double* W, int64_t n, int64_t ncols, int64_
 int gpx_transpose(gpx_handle h, const double* in, int64_t rows, int64_t cols, int64_t ld_in, double* out,
                   int64_t ld_out, void* stream);
 int gpx_set_mask(gpx_handle h, uint8_t* mask, const int64_t* idx_dev, uint8_t value, void* stream);
+/* history of a greedy run: picks[n] = rec global index, scores[n] = rec score, pivots[n] = rec[2] (var_D(p) + noise, the
+ * number whose smallness flags an ill-conditioned design), column n of the design factor U (each nullable) */
 int gpx_store_pivot(gpx_handle h, const double* rec, int64_t n, double* U, int64_t ldu, int64_t* picks,
-                    double* scores, void* stream);
+                    double* scores, double* pivots, void* stream);
+
+/* ---- N1  collectives.  NCCL is resolved at run time (dlopen of libnccl.so.2, preferring the copy the
+ * process already loaded); a caller that never shards never needs it.  One communicator per handle. --------------------- */
+#define GPX_COMM_ID_BYTES 128
+/* rank 0: fill id_host (GPX_COMM_ID_BYTES bytes) and hand it to every rank by any host channel */
+int gpx_comm_unique_id(void* id_host, int nbytes);
+int gpx_comm_init(gpx_handle h, const void* id_host, int rank, int nranks);
+int gpx_comm_destroy(gpx_handle h);
+int gpx_comm_size(gpx_handle h); /* 0 without a communicator */
+/* recv[r*count .. (r+1)*count) = rank r's send[0..count) : the pivot-record exchange of a sharded greedy step */
+int gpx_comm_allgather(gpx_handle h, const double* send, double* recv, int64_t count, void* stream);
+int gpx_comm_bcast(gpx_handle h, double* buf, int64_t count, int root, void* stream);
+int gpx_comm_allreduce_sum(gpx_handle h, double* buf, int64_t count, void* stream);
+
+/* ---- Whole greedy loops in one call: steps n_begin .. n_end-1 issued back to back on `stream`, no host round trip.
+ * The structs only carry device pointers and sizes the caller already owns (layouts as in the per-step entry points).
+ * With a communicator of more than one rank and rec_all != NULL every step exchanges the ranks' pivot records
+ * (ncclAllGather of 19+n doubles) and all ranks append the same winner. ---------------------------------------------- */
+typedef struct gpx_ivar_state {
+    const double* Xm;      /* integration points, d x ldm (replicated on every rank) */
+    int64_t M, ldm;
+    double* Wm;            /* ncap x ldm */
+    double* varM;          /* ldm */
+    const double* Ma_rows; /* prologue rows of the integration points (prepared side A or raw coordinates) */
+    const double* Xc;      /* local candidates, d x ldc */
+    int64_t C, ldc;
+    double* Wc;            /* ncap x ldc */
+    double* varC;          /* ldc */
+    const double* Cb_rows; /* prologue rows of the candidates (prepared side B or raw coordinates) */
+    int64_t ncap;          /* rows allocated in Wm / Wc */
+    int64_t index_offset;  /* global index of local candidate 0 */
+    int prologue;          /* GPX_PRO_EXPANDED | GPX_PRO_DIFF */
+    int nseg;              /* resident mode: gpx_cov_segments(M) */
+    double noise, zero_tol;
+    double* workspace;     /* gpx_score_ivar_workspace doubles */
+    double* scores;        /* ldc */
+    double* best;          /* 1 */
+    int64_t* idx;          /* 1 */
+    double* rec;           /* GPX_PIVOT_HDR + ncap */
+    double* rec_all;       /* comm_size x (GPX_PIVOT_HDR + ncap), or NULL */
+    double* rec_win;       /* GPX_PIVOT_HDR + ncap, or NULL */
+    double* U;             /* nullable: ncap x ldu design factor (K_DD + noise I = U^T U), grown column by column */
+    int64_t ldu;
+    int64_t* picks;        /* ncap */
+    double* pick_scores;   /* nullable, ncap */
+    double* pick_pivots;   /* nullable, ncap */
+    double* cov;           /* nullable: resident posterior covariance M x ldcov -> rank-1 update instead of the contraction */
+    int64_t ldcov, ldp;
+} gpx_ivar_state;
+
+/* discrete greedy IVAR (arg-min over c of costFunctionGP_IVAR.evaluate(design + [c]),
+ * experimentalDesign.py:79-117), steps n_begin .. n_end-1 */
+int gpx_ivar_greedy_run(gpx_handle h, const gpx_ivar_state* s, int64_t n_begin, int64_t n_end, void* stream);
+
+typedef struct gpx_var_state {
+    const double* X;       /* local pool, d x ld */
+    int64_t C, ld;
+    double* W;             /* ncap x ld */
+    double* var;           /* ld */
+    const double* weights; /* nullable, C */
+    int64_t ncap, index_offset;
+    double noise;          /* nugget of the pivoted factorisation: 0.0 for the reference driver (experimentalDesign.py:825) */
+    double* best;
+    int64_t* idx;
+    double* rec;
+    double* rec_all;
+    double* rec_win;
+    int64_t* picks;
+    double* pick_scores;
+    double* pick_pivots;
+} gpx_var_state;
+
+/* performGreedyVarExperimentalDesign (experimentalDesign.py:787-845), steps n_begin .. n_end-1 */
+int gpx_var_greedy_run(gpx_handle h, const gpx_var_state* s, int64_t n_begin, int64_t n_end, void* stream);
+
+/* sizeof(gpx_ivar_state) (which = 0) / sizeof(gpx_var_state) (which = 1) as compiled into the library */
+int64_t gpx_state_bytes(int which);
 
 /* ---- callers of the hot path (continuous optimisers, model fitting) --------------------------- */
 

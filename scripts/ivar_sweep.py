@@ -1,5 +1,6 @@
 """Time the IVAR scoring kernel (gpx_score_ivar) versus design size n on one GPU.
-usage: python scripts/ivar_sweep.py [d] [C] [M] [n1,n2,...]   -> gpurun_out/ivar_sweep.json"""
+usage: [GPX_IVAR_RING=0|1|2] [GPX_FORCE_DIFF=1] python scripts/ivar_sweep.py [d] [C] [M] [n1,n2,...]
+       -> gpurun_out/ivar_sweep_d<d>_ring<r>[_diff].json   (A/B runs of the ring geometry and the prologue form)"""
 import json
 import os
 import sys
@@ -17,6 +18,8 @@ C = int(sys.argv[2]) if len(sys.argv) > 2 else 100_000
 M = int(sys.argv[3]) if len(sys.argv) > 3 else 100_000
 ns = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0, 63, 255, 1023]
 dev = Device.get(0)
+ring = os.environ.get("GPX_IVAR_RING", "default")
+dev.force_diff_form = os.environ.get("GPX_FORCE_DIFF", "0") == "1"
 rng = np.random.default_rng(5)
 cl = [0.06, 0.09] if d == 2 else list(np.linspace(0.5, 1.5, d))
 kern = kernels.KernelSquaredExponential(cl, 1.0, d)
@@ -41,11 +44,12 @@ for n in ns:
     ms = e0.elapsed_time(e1) / reps
     # flops: contraction 2*M*n*C plus the Gram prologue 2*M*dpad*C on the same pipe
     dpad = (d + 3) // 4 * 4
-    row = {"d": d, "n": n, "C": C, "M": M, "ms": ms, "cand_per_s": C / ms * 1e3,
+    row = {"d": d, "n": n, "C": C, "M": M, "ms": ms, "cand_per_s": C / ms * 1e3, "ring": ring, "diff_form": dev.force_diff_form,
+           "prologue": int(eng.prologue()[0]), "scores_head": [float(v) for v in eng.scores[:8].cpu().numpy()],
            "tflops_contraction": 2.0 * M * n * C / ms / 1e9, "tflops_incl_prologue": 2.0 * M * (n + dpad) * C / ms / 1e9}
     print(json.dumps(row), flush=True)
     out.append(row)
     del eng
     torch.cuda.empty_cache()
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open(f"gpurun_out/ivar_sweep_d{d}.json", "w"), indent=1)
+json.dump(out, open(f"gpurun_out/ivar_sweep_d{d}_ring{ring}{'_diff' if dev.force_diff_form else ''}.json", "w"), indent=1)

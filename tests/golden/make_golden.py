@@ -234,11 +234,54 @@ def gen_greedy_mi(out):
         out[f"gmi/{ci}/invcov"] = cf.invcov
 
 
+def _cfg1_chunk(args):
+    """Worker of gen_cfg1: reference IVAR cost of design + [c] for a slice of the candidates."""
+    cl, noise, design, cand, mc, lo, hi = args
+    kern = rk.KernelSquaredExponential([cl], 1.0, 1)
+    gp = rgp.GP(kern, float(noise))
+    cf = red.costFunctionGP_IVAR(gp, design.shape[0] + 1, Space(1, None, None, noise=None), mcPoints=mc)
+    return np.array([cf.evaluate(np.vstack([design, cand[j:j + 1]])) for j in range(lo, hi)])
+
+
+def gen_cfg1(out):
+    """BASELINE.json configs[0] at FULL size through the unmodified reference: 1-D isotropic SE,
+    greedy IVAR design of 20 points from 1 000 candidates x 10 000 MC points, seed 1 -- (a) cl = 0.05, noise 1e-6 (the
+    well-conditioned measurement input) and (b) the demo.py:52-58 stress values cl = 0.3, noise 0.0, whose design Gram
+    reaches cond ~1e17.  The 20 x 1000 reference evaluations of a variant are independent within a step, so the
+    candidates are spread over worker processes; every number is still produced by
+    costFunctionGP_IVAR.evaluate (experimentalDesign.py:79-117)."""
+    import multiprocessing as mp
+    rng = np.random.default_rng(1)
+    cand = rng.uniform(-1.0, 1.0, (1000, 1))
+    mc = rng.uniform(-1.0, 1.0, (10000, 1))
+    out["cfg1/cand"] = cand
+    out["cfg1/mc"] = mc
+    nproc = max(1, min(8, (os.cpu_count() or 2)))
+    edges = np.linspace(0, cand.shape[0], nproc + 1).astype(int)
+    with mp.get_context("fork").Pool(nproc) as pool:
+        for tag, cl, noise, n in [("main", 0.05, 1e-6, 20), ("stress", 0.3, 0.0, 20)]:
+            kern = rk.KernelSquaredExponential([cl], 1.0, 1)
+            idx, costs, conds = [], np.zeros((n, cand.shape[0])), np.zeros(n)
+            for step in range(n):
+                design = cand[idx]
+                parts = pool.map(_cfg1_chunk, [(cl, noise, design, cand, mc, int(a), int(b))
+                                               for a, b in zip(edges[:-1], edges[1:])])
+                costs[step] = np.concatenate(parts)
+                idx.append(int(np.argmin(costs[step])))
+                conds[step] = np.linalg.cond(rku.calculateCovarianceMatrix(kern, cand[idx], float(noise)))
+                print(tag, "step", step, "pick", idx[-1], "cond %.3g" % conds[step], flush=True)
+            out[f"cfg1/{tag}/cl"] = np.float64(cl)
+            out[f"cfg1/{tag}/noise"] = np.float64(noise)
+            out[f"cfg1/{tag}/idx"] = np.array(idx, dtype=np.int64)
+            out[f"cfg1/{tag}/costs"] = costs
+            out[f"cfg1/{tag}/cond"] = conds
+
+
 def main():
     only = sys.argv[1:]
     for fname, gen in [("kernels.npz", gen_kernels), ("gram.npz", gen_gram), ("gp.npz", gen_gp),
                        ("greedy_var.npz", gen_greedy_var), ("greedy_ivar.npz", gen_greedy_ivar),
-                       ("greedy_mi.npz", gen_greedy_mi), ("next.npz", gen_next)]:
+                       ("greedy_mi.npz", gen_greedy_mi), ("next.npz", gen_next), ("cfg1.npz", gen_cfg1)]:
         if only and fname not in only:
             continue
         out = {}

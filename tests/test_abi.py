@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert len(funcs) >= 30
     for name in funcs:
         assert hasattr(_lib.lib, name), f"{name} declared in the header but not exported"
-    assert _lib.lib.gpx_version() == 100
+    assert _lib.lib.gpx_version() == _lib.GPX_VERSION == 200
 
 
 def test_ctypes_table_matches_header():

@@ -584,16 +584,19 @@ def test_score_ivar_unpadded_operands_use_the_generic_core(gx):
     Xm, Xc = up(mc.T.copy(), ldm), up(cand.T.copy(), ldc)
     Wm, Wc = up(w_m, ldm), up(w_c, ldc)
     vM, vC = up(var_m[None, :], ldm), up(var_c[None, :], ldc)
-    ma_rows, ma_s, cb_rows, cb_s = dev.zeros(16, ldm), dev.zeros(ldm), dev.zeros(16, ldc), dev.zeros(ldc)
-    gx.check(lib.gpx_prep_side(dev.h, 0, ptr(Xm), M, ldm, ptr(ma_rows), ptr(ma_s), ldm, dev.stream))
-    gx.check(lib.gpx_prep_side(dev.h, 1, ptr(Xc), Cn, ldc, ptr(cb_rows), ptr(cb_s), ldc, dev.stream))
+    ma_rows, cb_rows, mx = dev.zeros(16, ldm), dev.zeros(16, ldc), dev.zeros(1)
+    gx.check(lib.gpx_prep_side(dev.h, 0, ptr(Xm), M, ldm, ptr(ma_rows), ldm, ptr(mx), dev.stream))
+    assert 0.0 < mx.item() <= 5.0 + 1e-12  # max |alpha| = max sum x^2 on [-1,1]^5
+    gx.check(lib.gpx_prep_side(dev.h, 1, ptr(Xc), Cn, ldc, ptr(cb_rows), ldc, None, dev.stream))
     ws = dev.zeros(int(lib.gpx_score_ivar_workspace(dev.h, M, Cn)))
-    score, best, idx = dev.zeros(ldc), dev.zeros(1), dev.zeros(1, dtype=torch.int64)
-    gx.check(lib.gpx_score_ivar(dev.h, ptr(Wm), ldm, ptr(vM), ptr(ma_rows), ptr(ma_s), M, ptr(Wc), ldc, ptr(vC), ptr(cb_rows),
-                                ptr(cb_s), Cn, n, noise, 1e-13, None, ptr(ws), ptr(score), ptr(best), ptr(idx), dev.stream))
-    got = score[:Cn].cpu().numpy()
-    assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-9
-    assert int(idx.item()) == int(np.argmin(ref)) and best.item() == got.min()
+    # both prologue forms: prepared sides on the tensor pipe, and raw coordinates in difference form
+    for mode, ra, rb in [(gx._lib.PRO_EXPANDED, ma_rows, cb_rows), (gx._lib.PRO_DIFF, Xm, Xc)]:
+        score, best, idx = dev.zeros(ldc), dev.zeros(1), dev.zeros(1, dtype=torch.int64)
+        gx.check(lib.gpx_score_ivar(dev.h, mode, ptr(Wm), ldm, ptr(vM), ptr(ra), M, ptr(Wc), ldc, ptr(vC), ptr(rb), Cn, n,
+                                    noise, 1e-13, None, ptr(ws), ptr(score), ptr(best), ptr(idx), dev.stream))
+        got = score[:Cn].cpu().numpy()
+        assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-9, mode
+        assert int(idx.item()) == int(np.argmin(ref)) and best.item() == got.min()
 
 
 # ------------------------------------------------------------------------------------------------
