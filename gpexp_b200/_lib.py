@@ -86,6 +86,7 @@ SIGNATURES = {
     "gpx_append_row": [_p, _int, _p, _p, _p, _i64, _i64, _p, _i64, _i64, _p, _p],
     "gpx_argreduce": [_p, _p, _p, _p, _i64, _int, _p, _p, _p],
     "gpx_sum": [_p, _p, _i64, _p, _p],
+    "gpx_set_ivar_ring": [_p, _int],
     "gpx_score_ivar_workspace": [_p, _i64, _i64],
     "gpx_score_ivar": [_p, _int, _p, _i64, _p, _p, _i64, _p, _i64, _p, _p, _i64, _i64, _dbl, _dbl, _p, _p, _p, _p, _p, _p],
     "gpx_cov_segments": [_i64],

@@ -1,6 +1,7 @@
 // Handle lifetime, error reporting and kernel hyper-parameter set-up of the gpexp_b200 C ABI.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "gpx_common.cuh"
@@ -76,6 +77,10 @@ extern "C" int gpx_create(int device, gpx_handle* out) {
     memset(c, 0, sizeof(*c));
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    {
+        const char* e = getenv("GPX_IVAR_RING");
+        c->ivar_ring = (e && e[0] >= '0' && e[0] <= '2' && e[1] == 0) ? (e[0] - '0') : GPX_DEFAULT_IVAR_RING;
+    }
     bool ok = cudaMalloc(&c->red_val, GPX_RED_SLOTS * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&c->red_idx, GPX_RED_SLOTS * sizeof(int64_t)) == cudaSuccess &&
               cudaMalloc(&c->red_counter, 16 * sizeof(unsigned int)) == cudaSuccess &&

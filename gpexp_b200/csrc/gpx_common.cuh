@@ -51,7 +51,12 @@ struct gpx_context {
     // optional NCCL communicator (gpx_comm_init); the library resolves NCCL at run time, it does not link it
     void* nccl_comm;
     int comm_rank, comm_size;
+    int ivar_ring;            // ring geometry of ivar_ws_kernel (gpx_set_ivar_ring)
 };
+
+#ifndef GPX_DEFAULT_IVAR_RING
+#define GPX_DEFAULT_IVAR_RING 0
+#endif
 
 #define GPX_RED_SLOTS 2048
 

@@ -35,10 +35,6 @@
 
 #include "gpx_common.cuh"
 
-#ifndef GPX_DEFAULT_IVAR_RING
-#define GPX_DEFAULT_IVAR_RING 0
-#endif
-
 namespace {
 
 // expanded-form covariance with the table exp; tab already carries the signal variance
@@ -843,16 +839,6 @@ __global__ void __launch_bounds__(256, 1) sub_ws_kernel(const __grid_constant__ 
     }
 }
 
-// which ring the hot kernel runs on: 0 = RingSync, 1 = RingLag1, 2 = RingLag2.  GPX_IVAR_RING overrides (A/B runs).
-int ivar_ring() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("GPX_IVAR_RING");
-        v = (e && e[0] >= '0' && e[0] <= '2') ? (e[0] - '0') : GPX_DEFAULT_IVAR_RING;
-    }
-    return v;
-}
-
 template <int FAM, int PRO, class RING>
 int launch_ivar_ws_ring(gpx_handle h, const CoreArgs& a, dim3 grid, cudaStream_t st) {
     int rc = gpx_ensure_smem(h, (const void*)ivar_ws_kernel<FAM, PRO, RING>, RING::SMEM_BYTES, "ivar_ws");
@@ -864,7 +850,7 @@ int launch_ivar_ws_ring(gpx_handle h, const CoreArgs& a, dim3 grid, cudaStream_t
 template <int FAM, int PRO>
 int launch_ivar_ws(gpx_handle h, const CoreArgs& a, dim3 grid, cudaStream_t st) {
     // the lagged rings stage 16-row chunks: every prologue fits (EXPANDED <= 16 rows, DIFF <= 16 coordinates)
-    switch (ivar_ring()) {
+    switch (h->ivar_ring) {
         case 1: return launch_ivar_ws_ring<FAM, PRO, RingLag1>(h, a, grid, st);
         case 2: return launch_ivar_ws_ring<FAM, PRO, RingLag2>(h, a, grid, st);
         default: return launch_ivar_ws_ring<FAM, PRO, RingSync>(h, a, grid, st);
@@ -1173,6 +1159,14 @@ static int ivar_finalize_argmin(gpx_handle h, const double* partial, int nsplit,
                                                                  mask, score_out, h->red_val, h->red_idx, h->red_counter, best,
                                                                  idx);
     return gpx_check_launch("gpx_score_ivar finalize");
+}
+
+// ring geometry of the hot kernel: 0 = RingSync (32-row chunks, 3 stages), 1 / 2 = RingLag (16-row chunks, 6 stages,
+// group B one / two chunks behind group A).  Default GPX_DEFAULT_IVAR_RING, or the GPX_IVAR_RING environment variable.
+extern "C" int gpx_set_ivar_ring(gpx_handle h, int ring) {
+    GPX_REQUIRE(h != nullptr && ring >= 0 && ring <= 2, GPX_EINVAL, "ring must be 0, 1 or 2");
+    h->ivar_ring = ring;
+    return GPX_OK;
 }
 
 extern "C" int64_t gpx_score_ivar_workspace(gpx_handle h, int64_t M, int64_t C) {

@@ -185,6 +185,11 @@ int gpx_argreduce(gpx_handle h, const double* v, const double* weights, const ui
 /* Deterministic sum of n doubles (fixed tree order). */
 int gpx_sum(gpx_handle h, const double* v, int64_t n, double* out, void* stream);
 
+/* Ring geometry of the IVAR contraction kernel (A/B measurements; results are identical): 0 = 32-row chunks x 3 stages,
+ * all warps in step; 1 / 2 = 16-row chunks x 6 stages with the second warp group held 1 / 2 chunks behind the first so
+ * that one group's per-tile exp prologue overlaps the other's DMMA stream. */
+int gpx_set_ivar_ring(gpx_handle h, int ring);
+
 /* Workspace (doubles) gpx_score_ivar needs for C candidates. */
 int64_t gpx_score_ivar_workspace(gpx_handle h, int64_t M, int64_t C);
 

@@ -18,7 +18,7 @@ C = int(sys.argv[2]) if len(sys.argv) > 2 else 100_000
 M = int(sys.argv[3]) if len(sys.argv) > 3 else 100_000
 ns = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0, 63, 255, 1023]
 dev = Device.get(0)
-ring = os.environ.get("GPX_IVAR_RING", "default")
+ring = os.environ.get("GPX_IVAR_RING", "default")  # read by gpx_create
 dev.force_diff_form = os.environ.get("GPX_FORCE_DIFF", "0") == "1"
 rng = np.random.default_rng(5)
 cl = [0.06, 0.09] if d == 2 else list(np.linspace(0.5, 1.5, d))

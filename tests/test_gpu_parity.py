@@ -729,3 +729,239 @@ def test_dgemm_tn_sub_padded_tma_kernel(gx, shape):
         np.testing.assert_allclose(np.triu(got), np.triu(want), rtol=1e-12, atol=1e-12)
     # unpadded leading dimension is refused
     assert lib.gpx_dgemm_tn_sub_padded(dev.h, ptr(Ad), 2, ptr(Bd), ldb, ptr(Cd), ldc, max(I, 3), J, K, 0, dev.stream) == -2
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: BASELINE configs[0] at full size against the unmodified reference, conditioning guards, C-side loops
+# ------------------------------------------------------------------------------------------------
+def _cfg1(golden, tag):
+    z = golden("cfg1")
+    return (z["cfg1/cand"], z["cfg1/mc"], float(z[f"cfg1/{tag}/cl"]), float(z[f"cfg1/{tag}/noise"]),
+            z[f"cfg1/{tag}/idx"], z[f"cfg1/{tag}/costs"], z[f"cfg1/{tag}/cond"])
+
+
+def test_cfg1_full_size_golden(gx, golden):
+    """configs[0]: 1-D SE cl=0.05, 20 of 1 000 candidates x 10 000 MC points -- every one of the 20 x 1 000 costs of the
+    unmodified reference (costFunctionGP_IVAR.evaluate per candidate and step), through the public driver (C-side loop)
+    and through the traced step path."""
+    cand, mc, cl, noise, idx, ref_costs, _ = _cfg1(golden, "main")
+    from gpexp_b200 import kernels as K
+    k = K.KernelSquaredExponential([cl], 1.0, 1)
+    cf = gx.ed.costFunctionGP_IVAR(gx.gp.GP(k, noise), 1, gx.Space(1, None, None), mcPoints=mc)
+    for resident in (False, True):
+        got = gx.ed.performGreedyIVARExperimentalDesign(cf, cand, 20, returnIndices=True, resident=resident)
+        assert [int(i) for i in got] == [int(i) for i in idx], resident
+        want = ref_costs[np.arange(20), idx]
+        assert np.max(np.abs(cf.lastScores - want) / np.abs(want)) <= 1e-9
+        assert cf.illConditionedFrom is None and cf.lastPivots.shape == (20,)
+    fam, d, params = k._gpx_spec()
+    eng = gx.engine.GreedyIVAREngine(gx.dev, gx.dev.points(cand), gx.dev.points(mc), 20, noise, gx.engine.prior_scale(fam, params))
+    eng.score_trace = []
+    eng.run(20)
+    for s, c in enumerate(eng.score_trace):
+        assert np.max(np.abs(c - ref_costs[s]) / np.abs(ref_costs[s])) <= 1e-9, s
+
+
+def test_cfg1_demo_stress_variant_flags_ill_conditioning(gx, golden):
+    """demo.py:52-58 values (cl = 0.3, noise 0.0): the reference's own Gram reaches cond 3e11 at step 10 and 1e17 later
+    (fixture cfg1/stress/cond).  Contract: identical picks while cond <= ~1e7 (the documented first 10 steps), picked
+    costs within cond * 1e-13, and a GpxConditionWarning naming a step no later than the first pick that differs."""
+    import warnings
+    cand, mc, cl, noise, idx, ref_costs, cond = _cfg1(golden, "stress")
+    from gpexp_b200 import kernels as K
+    k = K.KernelSquaredExponential([cl], 1.0, 1)
+    cf = gx.ed.costFunctionGP_IVAR(gx.gp.GP(k, noise), 1, gx.Space(1, None, None), mcPoints=mc)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        got = [int(i) for i in gx.ed.performGreedyIVARExperimentalDesign(cf, cand, 20, returnIndices=True, resident=False)]
+    assert got[:10] == [int(i) for i in idx[:10]]
+    for s in range(10):
+        want = ref_costs[s, idx[s]]
+        assert abs(cf.lastScores[s] - want) <= max(1e-9, 1e-13 * cond[s]) * abs(want), s
+    first_diff = next((s for s in range(20) if got[s] != int(idx[s])), 20)
+    assert cf.illConditionedFrom is not None and cf.illConditionedFrom <= first_diff
+    assert any(issubclass(x.category, gx.engine.GpxConditionWarning) for x in w)
+    assert np.all(np.isfinite(cf.lastScores)) and np.all(np.isfinite(cf.lastPivots))
+
+
+def test_c_side_loop_equals_step_path(gx):
+    """gpx_ivar_greedy_run / gpx_var_greedy_run issue the same arithmetic as the per-step Python path: bit-identical
+    picks, scores and pivots, in contraction and resident mode."""
+    rng = np.random.default_rng(77)
+    cand, mc = rng.uniform(-1, 1, (2300, 2)), rng.uniform(-1, 1, (1700, 2))
+    k = bind(gx, "se_ard_2d_wide")
+    fam, d, params = k._gpx_spec()
+    for resident in (False, True):
+        out = []
+        for traced in (False, True):
+            eng = gx.engine.GreedyIVAREngine(gx.dev, gx.dev.points(cand), gx.dev.points(mc), 17, 1e-6,
+                                             gx.engine.prior_scale(fam, params), resident=resident)
+            if traced:
+                eng.score_trace = []
+            eng.run(17)
+            out.append((eng.indices(), eng.pick_scores[:17].cpu().numpy(), eng.pivots(), eng.U[:17, :17].cpu().numpy()))
+        for a, b in zip(out[0], out[1]):
+            assert np.array_equal(a, b), resident
+    pool = rng.uniform(-1, 1, (5001, 5))
+    bind(gx, "matern_5d")
+    w = rng.uniform(0.5, 1.5, 5001)
+    res = []
+    for traced in (False, True):
+        eng = gx.engine.GreedyVarEngine(gx.dev, gx.dev.points(pool), 33, weights=w)
+        if traced:
+            eng.score_trace = []
+        eng.run(33, progress=(lambda n: None) if not traced else None)
+        res.append((eng.indices(), eng.pick_scores[:33].cpu().numpy(), eng.pivots()))
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)
+
+
+def test_expanded_form_guard_and_centring(gx):
+    """k = f(alpha + beta + u.v) cancels |x|^2/cl^2 against x.y/cl^2.  (a) coordinates offset by 1e3
+    are centred and stay on the tensor-pipe prologue; (b) cl = 1e-3 exceeds the cancellation budget and is routed to the
+    difference form; both hold 1e-9 against the oracle; (c) forcing the forms apart on a benign case gives the same
+    scores; (d) the posterior-variance (TRSM) path takes the same decision."""
+    from gpexp_b200 import kernels as K
+    from gpexp_b200.device import prologue_operands
+    rng = np.random.default_rng(12)
+    L = gx._lib
+
+    def run(kern, ks, cand, mc, design, noise, expect_mode):
+        kern._bind(gx.dev)
+        fam, d, params = kern._gpx_spec()
+        eng = gx.engine.GreedyIVAREngine(gx.dev, gx.dev.points(cand), gx.dev.points(mc), max(len(design), 1), noise,
+                                         gx.engine.prior_scale(fam, params))
+        eng.load_design(gx.engine.DesignFactor(gx.dev, gx.dev.points(design), noise))
+        assert eng.prologue()[0] == expect_mode
+        eng.score()
+        w_m, var_m = orc.fast_design_state(ks, design, mc, noise)
+        w_c, var_c = orc.fast_design_state(ks, design, cand, noise)
+        ref = orc.fast_ivar_scores(ks, cand, mc, w_m, var_m, w_c, var_c, noise)
+        got = eng.scores[: len(cand)].cpu().numpy()
+        assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-9
+        assert int(eng.idx.item()) == int(np.argmin(ref))
+        return got
+
+    # (a) offset by 1e3, cl = 0.05 / 0.08: |alpha| would be ~1e8 without the centre
+    off = np.array([1e3, -2e3])
+    cand, mc = rng.uniform(-1, 1, (900, 2)) + off, rng.uniform(-1, 1, (1300, 2)) + off
+    design = cand[rng.permutation(900)[:40]]
+    run(K.KernelSquaredExponential([0.05, 0.08], 1.0, 2), orc.KernelSpec.se([0.05, 0.08], 1.0, 2), cand, mc, design, 1e-6,
+        L.PRO_EXPANDED)
+    run(K.KernelIsoMatern(0.7, 1.3, 2), orc.KernelSpec.matern32(0.7, 1.3, 2), cand, mc, design, 1e-6, L.PRO_EXPANDED)
+    # (b) cl = 1e-3 on [-1,1]: alpha up to 5e5 -> difference form
+    cand1, mc1 = rng.uniform(-1, 1, (1100, 1)), rng.uniform(-1, 1, (2500, 1))
+    design1 = cand1[rng.permutation(1100)[:30]]
+    run(K.KernelSquaredExponential([1e-3], 1.0, 1), orc.KernelSpec.se([1e-3], 1.0, 1), cand1, mc1, design1, 1e-6, L.PRO_DIFF)
+    # (c) same benign problem through both forms
+    cand2, mc2 = rng.uniform(-1, 1, (700, 3)), rng.uniform(-1, 1, (900, 3))
+    design2 = cand2[:25]
+    kern, ks = K.KernelMehlerND([0.6, 0.7, 0.5], 3), orc.KernelSpec.mehler([0.6, 0.7, 0.5], 3)
+    a = run(kern, ks, cand2, mc2, design2, 1e-2, L.PRO_EXPANDED)
+    gx.dev.force_diff_form = True
+    try:
+        b = run(kern, ks, cand2, mc2, design2, 1e-2, L.PRO_DIFF)
+        # (d) posterior variance through the TRSM path in difference form
+        g = gx.gp.GP(kern, 1e-2)
+        g.addNodesAndComputeCovariance(design2)
+        v_diff = g.evaluateVariance(mc2)
+    finally:
+        gx.dev.force_diff_form = False
+    assert np.max(np.abs(a - b) / np.abs(a)) <= 1e-11
+    g = gx.gp.GP(kern, 1e-2)
+    g.addNodesAndComputeCovariance(design2)
+    v_exp = g.evaluateVariance(mc2)
+    ref = orc.fast_posterior_variance(ks, design2, mc2, 1e-2)
+    scale = np.abs(ref).max()
+    assert np.max(np.abs(v_exp - ref)) <= 1e-10 * scale and np.max(np.abs(v_diff - ref)) <= 1e-10 * scale
+    # offset coordinates through GP.evaluateVariance as well (centre = mid-range of the query set)
+    kse, kso = K.KernelSquaredExponential([0.05, 0.08], 1.0, 2), orc.KernelSpec.se([0.05, 0.08], 1.0, 2)
+    g = gx.gp.GP(kse, 1e-6)
+    g.addNodesAndComputeCovariance(design)
+    v = g.evaluateVariance(mc)
+    ref = orc.fast_posterior_variance(kso, design, mc, 1e-6)
+    assert np.max(np.abs(v - ref)) <= 1e-9
+
+
+def test_ring_geometries_give_identical_scores(gx):
+    """The lagged-group rings (gpx_set_ivar_ring 1, 2) only reorder when the two warp groups work; every candidate's
+    sum is accumulated in the same order, so the scores are bit-identical to the in-step ring -- for d <= 14 (expanded
+    form), d = 16 (difference form) and a K tail that is not a multiple of the chunk."""
+    rng = np.random.default_rng(21)
+    for name, d, n in [("se_ard_2d", 2, 45), ("matern_5d", 5, 16), ("se_ard_10d", 10, 131)]:
+        k = bind(gx, name)
+        fam, _, params = k._gpx_spec()
+        cand, mc = rng.uniform(-1, 1, (1500, d)), rng.uniform(-1, 1, (2100, d))
+        eng = gx.engine.GreedyIVAREngine(gx.dev, gx.dev.points(cand), gx.dev.points(mc), n, 1e-4,
+                                         gx.engine.prior_scale(fam, params))
+        eng.load_design(gx.engine.DesignFactor(gx.dev, gx.dev.points(cand[:n]), 1e-4))
+        outs = []
+        try:
+            for ring in (0, 1, 2):
+                gx.check(gx.lib.gpx_set_ivar_ring(gx.dev.h, ring))
+                eng.score()
+                outs.append(eng.scores[:1500].cpu().numpy().copy())
+        finally:
+            gx.check(gx.lib.gpx_set_ivar_ring(gx.dev.h, 0))
+        assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2]), name
+        assert np.all(np.isfinite(outs[0]))
+
+
+def test_singular_gram_is_jittered_loudly(gx):
+    """noise 0.0 with a duplicated node makes the Gram singular; the reference's pinv shrugs, a Cholesky
+    factor does not exist.  The GP path warns, factors K + jitter and returns finite variances that agree with the
+    pseudo-inverse answer away from the null direction."""
+    import warnings
+    k = product_kernel("se_ard_2d_wide")
+    rng = np.random.default_rng(3)
+    nodes = rng.uniform(-1, 1, (12, 2))
+    nodes[7] = nodes[2]
+    q = rng.uniform(-1, 1, (200, 2))
+    g = gx.gp.GP(k, 0.0)
+    g.addNodesAndComputeCovariance(nodes)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        v = g.evaluateVariance(q)
+    assert any(issubclass(x.category, gx.engine.GpxConditionWarning) for x in w)
+    ks = spec("se_ard_2d_wide")
+    Kdd = ks.gram(nodes, nodes)
+    kq = ks.gram(nodes, q)
+    ref = ks.prior(q) - np.einsum("iq,ij,jq->q", kq, np.linalg.pinv(Kdd), kq)
+    assert np.all(np.isfinite(v)) and np.max(np.abs(v - ref)) <= 1e-6
+
+
+def test_argreduce_nan_wins_like_numpy(gx):
+    dev, lib, ptr, torch = gx.dev, gx.lib, gx.ptr, gx.torch
+    v = np.random.default_rng(5).standard_normal(70001)
+    v[[40000, 123]] = np.nan
+    best, idx = dev.zeros(1), dev.zeros(1, dtype=torch.int64)
+    for minimize in (0, 1):
+        gx.check(lib.gpx_argreduce(dev.h, ptr(dev.upload(v)), None, None, v.size, minimize, ptr(best), ptr(idx), dev.stream))
+        assert int(idx.item()) == 123 == int(np.argmax(v)) == int(np.argmin(v)) and np.isnan(best.item())
+
+
+def test_mi_cost_function_caches_the_factorisation(gx, golden):
+    """the reference's usage `for ind in options: costFuncMI.evaluate(ind, indKeep)` must not redo the O(|V|^3)
+    set-up per call.  Scores equal the golden ones; the engine object survives; add_candidates invalidates it."""
+    z = golden("greedy_mi")
+    name = str(z["gmi/1/name"])
+    k = product_kernel(name)
+    pool, noise = z["gmi/1/pool"], float(z["gmi/1/noise"])
+    idx, ref_scores = [int(i) for i in z["gmi/1/idx"]], z["gmi/1/scores"]
+    cf = gx.ed.costFunctionGP_MI(gx.gp.GP(k, noise), len(idx), gx.Space(k.dimension, None, None), nmc=len(pool), mcpoints=pool)
+    engines = set()
+    for step in range(1, 4):
+        keep = idx[:step]
+        options = [j for j in range(len(pool)) if j not in keep]
+        out = np.array([cf.evaluate(j, keep)[0] for j in options])
+        engines.add(id(cf._eval_engine))
+        ref = ref_scores[step][options]
+        assert np.max(np.abs(out - ref) / np.abs(ref)) <= 2e-8
+        assert options[int(np.argmax(out))] == idx[step]
+    assert len(engines) == 1
+    # a list that does not extend the previous one replays on the same factorisation
+    one = cf.evaluate(options[0], idx[:1])
+    assert abs(one[0] - ref_scores[1][options[0]]) <= 2e-8 * abs(ref_scores[1][options[0]]) and id(cf._eval_engine) in engines
+    np.testing.assert_allclose(cf.invcov, z["gmi/1/invcov"], rtol=0, atol=1e-9 * np.abs(z["gmi/1/invcov"]).max())
+    cf.add_candidates(len(pool) - 5, pool[:-5])
+    assert cf._eval_engine is None
