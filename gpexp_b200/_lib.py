@@ -113,14 +113,23 @@ SIGNATURES = {
     "gpx_var_greedy_run": [_p, C.POINTER(VarState), _i64, _i64, _p],
     "gpx_state_bytes": [_int],
     "gpx_se_dgram": [_p, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p],
-    "gpx_se_var_grad": [_p, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _p],
+    "gpx_se_var_grad": [_p, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p],
+    "gpx_se_loglike_grad_workspace": [_i64, _int],
+    "gpx_se_loglike_grad": [_p, _p, _i64, _i64, _p, _i64, _p, _p, _p, _p],
+    "gpx_gram_matvec_workspace": [_i64],
+    "gpx_gram_matvec": [_p, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _p],
+    "gpx_scale_rows_cols": [_p, _p, _i64, _i64, _i64, _p, _p, _dbl, _p, _i64, _p],
+    "gpx_diag_update": [_p, _p, _i64, _i64, _dbl, _p, _dbl, _p],
+    "gpx_axpby": [_p, _i64, _dbl, _p, _dbl, _p, _p],
+    "gpx_coldot": [_p, _p, _p, _i64, _i64, _i64, _p, _p, _p],
     "gpx_rowsum": [_p, _p, _i64, _i64, _i64, _dbl, _p, _p],
     "gpx_logdet_chol": [_p, _p, _i64, _i64, _p, _p],
     "gpx_bench_dmma": [_p, _i64, _p, _p],
     "gpx_bench_dfma": [_p, _i64, _p, _p],
 }
 _RESTYPES = {"gpx_last_error": C.c_char_p, "gpx_score_ivar_workspace": _i64, "gpx_mi_prec_column_workspace": _i64,
-             "gpx_state_bytes": _i64, "gpx_launch_count": _i64}
+             "gpx_state_bytes": _i64, "gpx_launch_count": _i64, "gpx_se_loglike_grad_workspace": _i64,
+             "gpx_gram_matvec_workspace": _i64}
 
 for _name, _args in SIGNATURES.items():
     _fn = getattr(lib, _name)  # AttributeError here == the .so does not export a declared symbol

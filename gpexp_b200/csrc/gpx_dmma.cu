@@ -30,8 +30,10 @@
 //   i_local = wm*32 + (t>>1)*16 + (lane>>2)*2 + (t&1)            t = 0..3  (A fragments)
 //   j_local = wn*64 + (u>>1)*16 + (lane>>2)*2 + (u&1)            u = 0..7  (B fragments, load side)
 //   accumulator (t,u,e) sits at column  wn*64 + (u>>1)*16 + ((lane&3)*2+e)*2 + (u&1)
+#include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "gpx_common.cuh"
 
@@ -449,39 +451,44 @@ __global__ void __launch_bounds__(Cfg::NT, 2)
 // the bulk copies of a chunk -- a ninth, dedicated producer warp would put three warps on one sub-partition and cap
 // everybody at 168 registers.  No CTA-wide barrier in the main loop.
 //
-// Ring geometries (template RING):
-//   RingSync  32-row chunks, 3 stages, 1 chunk ahead; all 8 warps consume the same chunk at (nearly) the same time and
-//             rotate as producers.  Both warps of a sub-partition therefore reach the per-tile exp prologue together, and
-//             the FP64 pipe idles on its dependency latencies.
-//   RingLag   16-row chunks, 6 stages, 2 ahead; the warps form two groups -- A = warps 0-3 (columns 0-63) and
-//             B = warps 4-7 (columns 64-127), one of each per sub-partition -- and group B is held LAG chunks behind
-//             group A (it may start chunk c only once every A warp has started chunk c+LAG; one extra mbarrier per
-//             stage).  A's prologue / epilogue then overlaps B's DMMA stream on the same sub-partition and vice versa.
-//             Only group A produces.
+// Ring geometries (template RING) and operand movement (template TMAP), selected per handle (gpx_set_ivar_ring):
+//   ring 0  32-row chunks, 3 stages, 1 chunk ahead, one cp.async.bulk (UBLKCP) per operand ROW: 65 copies per chunk
+//           issued from one lane of the producing warp (round-1 kernel).
+//   ring 1  same ring, but each operand chunk is ONE 2-D tensor-map TMA load (cp.async.bulk.tensor.2d, SASS UTMALDG):
+//           the box is 132 columns x 32 rows, so the hardware itself writes the padded, conflict-free 132-double row
+//           layout the fragment loads expect, and zero-fills the K tail (rows >= n) and the column overhang.
+//   ring 2  24-row chunks, 4 stages, 2 chunks ahead, tensor-map loads: more slack between a chunk's request and its
+//           first use.
+// Measured and dropped in round 2: holding the second warp group (columns 64-127) one or two 16-row chunks behind the
+// first so that one group's exp prologue overlaps the other's DMMA stream -- 174-178 ms against 162.7 ms at n = 255:
+// DMMA and DFMA share the FP64 pipe, so there is nothing to overlap, and the extra barrier costs.
 // Requires fully padded operands: lda, ldb multiples of 128 covering whole tiles (the engines guarantee it).
 // ---------------------------------------------------------------------------------------------
 constexpr int WS_BM = 128;
 constexpr int WS_LD = 132;
 
-template <int BK_, int STAGES_, int AHEAD_, int LAG_>
+template <int BK_, int STAGES_, int AHEAD_>
 struct Ring {
     static constexpr int RBK = BK_;                    // K rows per chunk
     static constexpr int KSTEPS = BK_ / 4;
-    static constexpr int STAGE = BK_ * 2 * WS_LD;      // doubles
+    static constexpr int STAGE = BK_ * 2 * WS_LD;      // doubles (a multiple of 16: every stage starts 128-byte aligned)
     static constexpr int NSTAGES = STAGES_;            // ring depth
-    static constexpr int AHEAD = AHEAD_;               // chunks in flight ahead of the (leading) consumers
-    static constexpr int LAG = LAG_;                   // chunks group B trails group A by (0: one group)
-    static constexpr int SMEM_DOUBLES = STAGES_ * STAGE + 4 * BN + 3 * STAGES_ + 256;
+    static constexpr int AHEAD = AHEAD_;               // chunks in flight ahead of the consumers
+    static constexpr int SMEM_DOUBLES = STAGES_ * STAGE + 4 * BN + 2 * STAGES_ + 256;
     static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES * sizeof(double);
-    static_assert(LAG_ == 0 || AHEAD_ + LAG_ <= STAGES_ - 2, "the refilled stage must have been released a chunk ago");
-    static_assert(AHEAD_ <= 4, "initial chunks are issued by the first warps of group A");
+    static_assert(AHEAD_ <= STAGES_ - 2, "the refilled stage must have been released a whole chunk ago");
+    static_assert((BK_ * WS_LD) % 16 == 0, "operand halves of a stage must be 128-byte aligned for TMA");
 };
 // Measured on B200, round 1 (n = 2047 / n = 255, C = M = 100k): 16 rows x 6 stages, 3 ahead: 34.18 TFLOP/s / 165.5 ms;
 // 32 rows x 3 stages, 1 ahead: 34.70 / 165.3 ms; 32 x 3, 2 ahead: 23.7 / 240 ms (the refilled stage must have been
 // released at least one whole chunk ago, or the producing warp blocks on the slowest consumer).
-using RingSync = Ring<32, 3, 1, 0>;
-using RingLag1 = Ring<16, 6, 2, 1>;
-using RingLag2 = Ring<16, 6, 2, 2>;
+using RingSync = Ring<32, 3, 1>;
+using RingDeep = Ring<24, 4, 2>;
+
+// tensor maps of the four operand streams of one IVAR launch (boxes: 132 columns x chunk rows)
+struct alignas(64) TmaMaps {
+    CUtensorMap a_main, b_main, a_pro, b_pro;
+};
 
 // sub_ws_kernel keeps the round-1 ring
 constexpr int WS_BK = RingSync::RBK;
@@ -519,6 +526,14 @@ __device__ __forceinline__ void bulk_g2s(double* dst, const double* src, unsigne
                  : "memory");
 }
 
+__device__ __forceinline__ void tma_load_2d(double* dst, const CUtensorMap* tm, int col, int row, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(col), "r"(row), "r"(smem_u32(bar))
+        : "memory");
+}
+
 __device__ __forceinline__ void load_frags_ws(double (&af)[4], double (&bf)[8], const double* pa, const double* pb, int ks) {
 #pragma unroll
     for (int t2 = 0; t2 < 2; ++t2) {
@@ -534,16 +549,16 @@ __device__ __forceinline__ void load_frags_ws(double (&af)[4], double (&bf)[8], 
     }
 }
 
-template <int FAM, int PRO, class RING>
-__global__ void __launch_bounds__(256, 1) ivar_ws_kernel(const __grid_constant__ CoreArgs a, const __grid_constant__ KParams kp) {
+template <int FAM, int PRO, class RING, bool TMAP>
+__global__ void __launch_bounds__(256, 1) ivar_ws_kernel(const __grid_constant__ CoreArgs a, const __grid_constant__ KParams kp,
+                                                         const __grid_constant__ TmaMaps maps) {
     constexpr int BM = WS_BM, LD = WS_LD, NW = 8;
-    constexpr int RBK = RING::RBK, NST = RING::NSTAGES, AHEAD = RING::AHEAD, LAG = RING::LAG;
-    extern __shared__ __align__(16) double smem[];
+    constexpr int RBK = RING::RBK, NST = RING::NSTAGES, AHEAD = RING::AHEAD;
+    extern __shared__ __align__(128) double smem[];
     double* s_red = smem + NST * RING::STAGE;
     uint64_t* full = reinterpret_cast<uint64_t*>(s_red + 4 * BN);
     uint64_t* empty = full + NST;
-    uint64_t* astart = empty + NST;                                  // RingLag: group A has started the chunk of this stage
-    double* s_tab = reinterpret_cast<double*>(astart + NST);         // signal * 2^(j/256)
+    double* s_tab = reinterpret_cast<double*>(empty + NST);          // signal * 2^(j/256)
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -574,7 +589,6 @@ __global__ void __launch_bounds__(256, 1) ivar_ws_kernel(const __grid_constant__
         for (int s = 0; s < NST; ++s) {
             mbar_init(full + s, 1);
             mbar_init(empty + s, NW);
-            mbar_init(astart + s, 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -611,6 +625,19 @@ __global__ void __launch_bounds__(256, 1) ivar_ws_kernel(const __grid_constant__
         }
         double* stA = smem + s * RING::STAGE;
         double* stB = stA + RBK * LD;
+        if (TMAP) {
+            // one 2-D tensor-map load per operand: the 132-column box lands as the padded rows the fragment loads expect;
+            // rows beyond the operand (K tail) and columns beyond its leading dimension are zero-filled by the TMA unit
+            if (lane == 0) {
+                const bool pro = pch == 0;
+                const int brows = pro ? a.prows : RBK;
+                mbar_arrive_expect_tx(full + s, (unsigned int)brows * 2u * LD * 8u);
+                tma_load_2d(stA, pro ? &maps.a_pro : &maps.a_main, (int)i0, pro ? 0 : (pch - 1) * RBK, full + s);
+                tma_load_2d(stB, pro ? &maps.b_pro : &maps.b_main, (int)j0, pro ? 0 : (pch - 1) * RBK, full + s);
+            }
+            __syncwarp();
+            return;
+        }
         if (krows < ksteps * 4) {
             // K tail: rows the DMMAs will read but the operand does not have -> explicit zeros (lane -> column pair)
             for (int r = krows; r < ksteps * 4; ++r) {
@@ -632,11 +659,7 @@ __global__ void __launch_bounds__(256, 1) ivar_ws_kernel(const __grid_constant__
         }
         __syncwarp();
     };
-    if (LAG == 0) {
-        if (warp < AHEAD) produce(warp);
-    } else {
-        if (wn == 0 && wm < AHEAD) produce(wm);
-    }
+    if (warp < AHEAD) produce(warp);
 
     {
         double acc[4][8][2];
@@ -648,13 +671,7 @@ __global__ void __launch_bounds__(256, 1) ivar_ws_kernel(const __grid_constant__
             const int s = g % NST;
             const unsigned int ph = (unsigned int)(g / NST) & 1u;
             const int64_t i0 = (it_begin + tl) * BM;
-            if (LAG == 0) {
-                if (warp == (g & (NW - 1))) produce(g + AHEAD);
-            } else {
-                if (wn == 0 && wm == (g & 3)) produce(g + AHEAD);
-                // group B stays LAG chunks behind group A (not enforced over the last LAG chunks of the CTA)
-                if (wn == 1 && g + LAG < G) mbar_wait(astart + (g + LAG) % NST, (unsigned int)((g + LAG) / NST) & 1u);
-            }
+            if (warp == (g & (NW - 1))) produce(g + AHEAD);
             if (ch == 0 && PRO != PRO_DIFF) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
@@ -662,10 +679,6 @@ __global__ void __launch_bounds__(256, 1) ivar_ws_kernel(const __grid_constant__
                     for (int u = 0; u < 8; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
             }
             mbar_wait(full + s, ph);
-            if (LAG > 0 && wn == 0) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(astart + s);
-            }
             const double* pa = smem + s * RING::STAGE + fa;
             const double* pb = smem + s * RING::STAGE + fb;
             if (ch == 0 && PRO == PRO_DIFF) {
@@ -680,11 +693,20 @@ __global__ void __launch_bounds__(256, 1) ivar_ws_kernel(const __grid_constant__
                     ksteps = rem >= RBK ? RING::KSTEPS : ((rem + 3) >> 2);
                 }
                 // single-buffered fragments: the other warp of the sub-partition covers the LDS latency (double
-                // buffering measured identical in round 1: 34.44 vs 34.43 TFLOP/s at n = 4095)
+                // buffering measured identical in round 1: 34.44 vs 34.43 TFLOP/s at n = 4095).  Whole chunks run fully
+                // unrolled (constant LDS offsets, no loop arithmetic between the DMMA groups).
+                if (ksteps == RING::KSTEPS) {
+#pragma unroll
+                    for (int ks = 0; ks < RING::KSTEPS; ++ks) {
+                        load_frags_ws(af0, bf0, pa, pb, ks);
+                        mma_tile(acc, af0, bf0);
+                    }
+                } else {
 #pragma unroll 1
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    load_frags_ws(af0, bf0, pa, pb, ks);
-                    mma_tile(acc, af0, bf0);
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        load_frags_ws(af0, bf0, pa, pb, ks);
+                        mma_tile(acc, af0, bf0);
+                    }
                 }
                 if (ch == 0) {
                     // covariance from the expanded form (alpha, beta are two rows of the contraction); accumulators
@@ -839,21 +861,71 @@ __global__ void __launch_bounds__(256, 1) sub_ws_kernel(const __grid_constant__ 
     }
 }
 
-template <int FAM, int PRO, class RING>
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// rows x ld doubles, row-major, box = 132 columns x box_rows; out-of-range elements read as zero
+int make_map(CUtensorMap* m, const double* base, int64_t ld, int64_t rows, int box_rows) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) {
+        gpx_set_error("ivar_ws: cuTensorMapEncodeTiled is not available from this driver");
+        return GPX_EINVAL;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)(rows > 0 ? rows : 1)};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)WS_LD, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        gpx_set_error("ivar_ws: cuTensorMapEncodeTiled failed with CUresult %d (ld %lld, rows %lld, box rows %d)", (int)r,
+                      (long long)ld, (long long)rows, box_rows);
+        return GPX_EINVAL;
+    }
+    return GPX_OK;
+}
+
+template <int FAM, int PRO, class RING, bool TMAP>
 int launch_ivar_ws_ring(gpx_handle h, const CoreArgs& a, dim3 grid, cudaStream_t st) {
-    int rc = gpx_ensure_smem(h, (const void*)ivar_ws_kernel<FAM, PRO, RING>, RING::SMEM_BYTES, "ivar_ws");
+    TmaMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    int rc;
+    if (TMAP) {
+        // the K extent of the main maps is the CURRENT design size: rows >= n are zero-filled, never read
+        if (a.K > 0) {
+            if ((rc = make_map(&maps.a_main, a.A, a.lda, a.K, RING::RBK))) return rc;
+            if ((rc = make_map(&maps.b_main, a.B, a.ldb, a.K, RING::RBK))) return rc;
+        }
+        if ((rc = make_map(&maps.a_pro, a.Ap, a.lda, a.prows, a.prows))) return rc;
+        if ((rc = make_map(&maps.b_pro, a.Bp, a.ldb, a.prows, a.prows))) return rc;
+    }
+    rc = gpx_ensure_smem(h, (const void*)ivar_ws_kernel<FAM, PRO, RING, TMAP>, RING::SMEM_BYTES, "ivar_ws");
     if (rc) return rc;
-    ivar_ws_kernel<FAM, PRO, RING><<<grid, 256, RING::SMEM_BYTES, st>>>(a, h->kp);
+    ivar_ws_kernel<FAM, PRO, RING, TMAP><<<grid, 256, RING::SMEM_BYTES, st>>>(a, h->kp, maps);
     return gpx_check_launch("ivar_ws");
 }
 
 template <int FAM, int PRO>
 int launch_ivar_ws(gpx_handle h, const CoreArgs& a, dim3 grid, cudaStream_t st) {
-    // the lagged rings stage 16-row chunks: every prologue fits (EXPANDED <= 16 rows, DIFF <= 16 coordinates)
+    // every prologue fits one chunk of every ring (EXPANDED <= 16 rows, DIFF <= 16 coordinates, chunks >= 24 rows)
     switch (h->ivar_ring) {
-        case 1: return launch_ivar_ws_ring<FAM, PRO, RingLag1>(h, a, grid, st);
-        case 2: return launch_ivar_ws_ring<FAM, PRO, RingLag2>(h, a, grid, st);
-        default: return launch_ivar_ws_ring<FAM, PRO, RingSync>(h, a, grid, st);
+        case 1: return launch_ivar_ws_ring<FAM, PRO, RingSync, true>(h, a, grid, st);
+        case 2: return launch_ivar_ws_ring<FAM, PRO, RingDeep, true>(h, a, grid, st);
+        default: return launch_ivar_ws_ring<FAM, PRO, RingSync, false>(h, a, grid, st);
     }
 }
 
@@ -1161,8 +1233,9 @@ static int ivar_finalize_argmin(gpx_handle h, const double* partial, int nsplit,
     return gpx_check_launch("gpx_score_ivar finalize");
 }
 
-// ring geometry of the hot kernel: 0 = RingSync (32-row chunks, 3 stages), 1 / 2 = RingLag (16-row chunks, 6 stages,
-// group B one / two chunks behind group A).  Default GPX_DEFAULT_IVAR_RING, or the GPX_IVAR_RING environment variable.
+// ring / operand movement of the hot kernel: 0 = 32-row chunks x 3 stages, per-row bulk copies; 1 = same ring, one 2-D
+// tensor-map load per operand chunk; 2 = 24-row chunks x 4 stages, 2 ahead, tensor-map loads.
+// Default GPX_DEFAULT_IVAR_RING, or the GPX_IVAR_RING environment variable.
 extern "C" int gpx_set_ivar_ring(gpx_handle h, int ring) {
     GPX_REQUIRE(h != nullptr && ring >= 0 && ring <= 2, GPX_EINVAL, "ring must be 0, 1 or 2");
     h->ivar_ring = ring;

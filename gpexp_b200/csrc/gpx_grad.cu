@@ -40,12 +40,15 @@ extern "C" int gpx_se_dgram(gpx_handle h, const double* X, int64_t nx, int64_t l
     return gpx_check_launch("gpx_se_dgram");
 }
 
-// out[(j*D + k), m] = 2 * At[j, m] * ( D(x_m, p_j)[k] - Qneg[(j*D + k), m] )          gp.py:322-340 restated
+// out[(j*D + k), m] = 2 * At[j, m] * ( D(x_m, p_j)[k] - Qneg[(j*D + k), m] ) - At[j, m]^2 * diag[j*D + k]
+//     gp.py:322-340 restated; diag (nullable) = d noise(p_j) / d p_j[k], the diagonal of the reference's symmetric
+//     dSigdXreal in the heteroscedastic branch (gp.py:314-318, :334-336) -- zero for a constant noise.
 template <int D>
 __global__ void __launch_bounds__(256) se_var_grad_kernel(const __grid_constant__ KParams kp, const double* __restrict__ P,
                                                            int64_t n, int64_t ldp, const double* __restrict__ X, int64_t M,
                                                            int64_t ldx, const double* __restrict__ At,
-                                                           const double* __restrict__ Qneg, double* __restrict__ out) {
+                                                           const double* __restrict__ Qneg, const double* __restrict__ diag,
+                                                           double* __restrict__ out) {
     const int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x;
     const int64_t j = blockIdx.y;
     if (m >= M || j >= n) return;
@@ -56,24 +59,27 @@ __global__ void __launch_bounds__(256) se_var_grad_kernel(const __grid_constant_
         acc = fma(df[q] * df[q], kp.a[q], acc);
     }
     const double kv = kp.signal * exp(-0.5 * acc);
-    const double a2 = 2.0 * At[j * ldx + m];
+    const double at = At[j * ldx + m];
+    const double a2 = 2.0 * at;
 #pragma unroll
     for (int q = 0; q < D; ++q) {
         const int64_t r = j * D + q;
         const double dk = -kp.signal * df[q] * kp.a[q] * kv;
-        out[r * ldx + m] = a2 * (dk - Qneg[r * ldx + m]);
+        double v = a2 * (dk - Qneg[r * ldx + m]);
+        if (diag) v = fma(-at * at, diag[r], v);
+        out[r * ldx + m] = v;
     }
 }
 
 extern "C" int gpx_se_var_grad(gpx_handle h, const double* P, int64_t n, int64_t ldp, const double* X, int64_t M, int64_t ldx,
-                               const double* At, const double* Qneg, double* out, void* stream) {
+                               const double* At, const double* Qneg, const double* diag, double* out, void* stream) {
     GPX_NEED_KERNEL(h);
     GPX_REQUIRE(h->kp.family == GPX_SE, GPX_EINVAL, "kernel derivatives exist for the squared-exponential family only");
     GPX_REQUIRE(n >= 0 && M >= 0, GPX_EINVAL, "bad sizes");
     if (n == 0 || M == 0) return GPX_OK;
     GPX_REQUIRE(P && X && At && Qneg && out && n <= 65535, GPX_EINVAL, "bad arguments");
     dim3 grid((unsigned)((M + 255) / 256), (unsigned)n);
-    GPX_DISPATCH_DIM(h->kp.d, (se_var_grad_kernel<D><<<grid, 256, 0, (cudaStream_t)stream>>>(h->kp, P, n, ldp, X, M, ldx, At, Qneg, out)));
+    GPX_DISPATCH_DIM(h->kp.d, (se_var_grad_kernel<D><<<grid, 256, 0, (cudaStream_t)stream>>>(h->kp, P, n, ldp, X, M, ldx, At, Qneg, diag, out)));
     return gpx_check_launch("gpx_se_var_grad");
 }
 

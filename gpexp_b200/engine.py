@@ -261,11 +261,17 @@ class DesignFactor:
             self._cov = self.U.clone()
             check(lib.gpx_potrf(dev.h, ptr(self.U), n, self.ldu, ptr(self.info), dev.stream), "gpx_potrf")
             bad = int(self.info.item())
+            scale = float(torch.diagonal(self._cov[:n, :n]).abs().max().item())
+            if not bad:
+                # a pivot that survives only as round-off (U_ii^2 <= 1e-13 x the largest diagonal entry) is a numerically
+                # singular Gram as well: cond >~ 1e13, everything solved against this factor would be noise
+                piv = torch.diagonal(self.U[:n, :n]) ** 2
+                if not bool(torch.isfinite(piv).all()) or float(piv.min().item()) <= 1e-13 * scale:
+                    bad = int(torch.argmin(torch.nan_to_num(piv, nan=-1.0)).item()) + 1
             if bad:
                 # The reference pseudo-inverts (np.linalg.pinv, gp.py:181) and so tolerates numerically singular Grams
                 # (noise 0 with duplicate or nearly dependent nodes); a Cholesky factor does not exist there.  Retry once
                 # with a jitter at the level of pinv's own cut-off region, loudly; fail if that is not enough.
-                scale = float(torch.diagonal(self._cov[:n, :n]).abs().max().item())
                 self.jitter = 1e-10 * scale
                 warnings.warn(f"Gram matrix is not numerically positive definite (pivot {bad - 1} of {n}); factoring "
                               f"K + {self.jitter:.3e} I instead -- results near the null directions differ from a "
@@ -334,9 +340,14 @@ class DesignFactor:
         check(lib.gpx_colsumsq(dev.h, ptr(B), self.n, 1, 2, None, ptr(out), dev.stream), "gpx_colsumsq")
         return float(out[0].item())
 
-    def variance_gradient(self, X: PointSet):
+    def variance_gradient(self, X: PointSet, noise_grad=None, same_location=None):
         """(n*d) x X.ld device matrix  out[j*d+k, m] = d var(x_m) / d design[j,k]  as GP.evaluateVarianceDerivative
-        (gp.py:282-341) defines it.  Squared-exponential kernels only."""
+        (gp.py:282-341) defines it.  Squared-exponential kernels only.
+
+        Heteroscedastic branch (gp.py:314-318): noise_grad[j,k] = d noise(p_j)/d p_j[k] enters the derivative of the
+        design Gram at every pair of coincident design points -- same_location[z,j] true where p_z == p_j (the diagonal
+        for distinct points) -- i.e. E[z, j*d+k] = same[z,j] * noise_grad[j,k] is added to dK/dp before the contraction and
+        the doubly counted diagonal is taken out again inside gpx_se_var_grad."""
         dev, D = self.dev, self.design
         n, d = self.n, D.d
         W, _ = self.solve_gram(X, want_var=False)
@@ -344,22 +355,157 @@ class DesignFactor:
         ldn = roundup(n * d)
         dct = dev.zeros(max(n, 1), ldn)
         check(lib.gpx_se_dgram(dev.h, ptr(D.X), n, D.ld, ptr(D.X), n, D.ld, ptr(dct), ldn, dev.stream), "gpx_se_dgram")
+        diag = None
+        if noise_grad is not None:
+            ng = np.asarray(noise_grad, dtype=np.float64).reshape(n, d)
+            same = np.eye(n, dtype=bool) if same_location is None else np.asarray(same_location, dtype=bool)
+            E = np.zeros((n, ldn))
+            E[:, : n * d] = (same[:, :, None] * ng[None, :, :]).reshape(n, n * d)
+            check(lib.gpx_axpby(dev.h, n * ldn, 1.0, ptr(dev.upload(E)), 1.0, ptr(dct), dev.stream), "gpx_axpby")
+            diag = dev.upload(ng.reshape(n * d))
         qneg = dev.zeros(max(n * d, 1), X.ld)
         check(lib.gpx_dgemm_tn_sub(dev.h, ptr(dct), ldn, ptr(W), X.ld, ptr(qneg), X.ld, n * d, X.n, n, 0, dev.stream),
               "gpx_dgemm_tn_sub")
         out = dev.zeros(max(n * d, 1), X.ld)
-        check(lib.gpx_se_var_grad(dev.h, ptr(D.X), n, D.ld, ptr(X.X), X.n, X.ld, ptr(W), ptr(qneg), ptr(out), dev.stream),
-              "gpx_se_var_grad")
+        check(lib.gpx_se_var_grad(dev.h, ptr(D.X), n, D.ld, ptr(X.X), X.n, X.ld, ptr(W), ptr(qneg), ptr(diag), ptr(out),
+                                  dev.stream), "gpx_se_var_grad")
         return out
 
-    def precision(self) -> np.ndarray:
-        """(U^T U)^-1 as a dense matrix: U^-1 (U^-T I)."""
+    def precision_device(self):
+        """(U^T U)^-1 as a dense n x roundup(n) device matrix: U^-1 (U^-T I)."""
         dev, n = self.dev, self.n
         ld = roundup(n)
         Y = dev.zeros(max(n, 1), ld)
         check(lib.gpx_trtri_t(dev.h, ptr(self.U), n, self.ldu, ptr(Y), ld, dev.stream), "gpx_trtri_t")
         check(lib.gpx_trsm_back(dev.h, ptr(self.Ut()), n, self.ldu, ptr(Y), n, ld, dev.stream), "gpx_trsm_back")
-        return Y[:n, :n].cpu().numpy()
+        return Y
+
+    def precision(self) -> np.ndarray:
+        return self.precision_device()[: self.n, : self.n].cpu().numpy()
+
+    def loglike_gradient(self, y: np.ndarray) -> np.ndarray:
+        """1/2 tr((alpha alpha^T - P) dK/dtheta) for theta = cl_0..cl_{d-1}, signalSize, noise (bare trace for the
+        noise entry), squared-exponential kernels (gp.py:447-468)."""
+        dev, D, n = self.dev, self.design, self.n
+        P = self.precision_device()
+        alpha = dev.upload(self.solve_vector(y))
+        ws = dev.zeros(max(int(lib.gpx_se_loglike_grad_workspace(n, D.d)), 1))
+        out = dev.zeros(D.d + 2)
+        check(lib.gpx_se_loglike_grad(dev.h, ptr(D.X), n, D.ld, ptr(P), P.shape[1], ptr(alpha), ptr(ws), ptr(out), dev.stream),
+              "gpx_se_loglike_grad")
+        return out.cpu().numpy()
+
+
+class FitcFactor:
+    """FITC sparse-GP covariance and precision of a design (gp_kernel_utilities.py:70-104, gp.py:182-208), all on the
+    device:  Q = K_fu K_uu^-1 K_uf,  G = diag(K_ff + noise - Q),  cov = Q + G,
+             precision = G^-1 - G^-1 K_fu (K_uu + K_uf G^-1 K_fu)^-1 K_uf G^-1      (Woodbury).
+    The reference pseudo-inverts K_uu and inverts the inner matrix; here both are Cholesky factors (K_uu carries the
+    noise on its diagonal, gp.py:193)."""
+
+    def __init__(self, dev: Device, design: PointSet, inducing: PointSet, noise: float):
+        self.dev, self.design, self.inducing = dev, design, inducing
+        n, nu, st = design.n, inducing.n, dev.stream
+        self.n = n
+        ld = design.ld
+        self.ld = ld
+        uu = DesignFactor(dev, inducing, float(noise))          # K_uu + noise I = U_u^T U_u
+        if uu.jitter:
+            warnings.warn("FITC: inducing-point Gram was jittered", GpxConditionWarning, stacklevel=3)
+        # A = U_u^-T K_uf   (nu x n): Q = A^T A, diag(Q) = column sums of squares
+        A = dev.zeros(max(nu, 1), ld)
+        check(lib.gpx_gram(dev.h, ptr(inducing.X), nu, inducing.ld, ptr(design.X), n, ld, ptr(A), ld, 0, None, 0.0, st), "gpx_gram")
+        Kuf = A.clone()
+        check(lib.gpx_trsm(dev.h, ptr(uu.U), nu, uu.ldu, ptr(A), n, ld, st), "gpx_trsm")
+        g = dev.zeros(ld)
+        check(lib.gpx_prior_diag(dev.h, ptr(design.X), n, ld, ptr(g), st), "gpx_prior_diag")
+        check(lib.gpx_colsumsq(dev.h, ptr(A), nu, n, ld, ptr(g), ptr(g), st), "gpx_colsumsq")     # k(x,x) - Q_ii
+        gh = g[:n].cpu().numpy() + float(noise)                                                  # + noise (gp.py:203-204)
+        g = dev.upload(np.concatenate([gh, np.ones(ld - n)]))
+        ginv = dev.upload(np.concatenate([1.0 / (gh + 1e-12), np.zeros(ld - n)]))                # gp.py:207
+        # cov = Q + G = A^T A + diag(g)
+        cov = dev.zeros(max(n, 1), ld)
+        check(lib.gpx_dgemm_tn_sub(dev.h, ptr(A), ld, ptr(A), ld, ptr(cov), ld, n, n, nu, 0, st), "gpx_dgemm_tn_sub")
+        check(lib.gpx_scale_rows_cols(dev.h, ptr(cov), n, n, ld, None, None, -1.0, ptr(cov), ld, st), "gpx_scale_rows_cols")
+        check(lib.gpx_diag_update(dev.h, ptr(cov), n, ld, 1.0, ptr(g), 0.0, st), "gpx_diag_update")
+        self._cov = cov
+        # S = K_uu + K_uf G^-1 K_fu   (nu x nu), contraction index = design points (K-major operands: K_fu rows)
+        ldu = inducing.ld
+        Kfu = dev.zeros(max(n, 1), ldu)
+        check(lib.gpx_gram(dev.h, ptr(design.X), n, ld, ptr(inducing.X), nu, ldu, ptr(Kfu), ldu, 0, None, 0.0, st), "gpx_gram")
+        Kfu_s = dev.zeros(max(n, 1), ldu)
+        check(lib.gpx_scale_rows_cols(dev.h, ptr(Kfu), n, nu, ldu, ptr(ginv), None, -1.0, ptr(Kfu_s), ldu, st), "gpx_scale_rows_cols")
+        S = uu._cov.clone()
+        check(lib.gpx_dgemm_tn_sub(dev.h, ptr(Kfu_s), ldu, ptr(Kfu), ldu, ptr(S), uu.ldu, nu, nu, n, 0, st), "gpx_dgemm_tn_sub")
+        info = dev.zeros(1, dtype=torch.int32)
+        check(lib.gpx_potrf(dev.h, ptr(S), nu, uu.ldu, ptr(info), st), "gpx_potrf")
+        if int(info.item()):
+            raise GpxError(f"FITC: inner Woodbury matrix is not positive definite (pivot {int(info.item()) - 1})")
+        # T = U_s^-T (K_uf G^-1)  ;  precision = G^-1 - T^T T
+        T = dev.zeros(max(nu, 1), ld)
+        check(lib.gpx_scale_rows_cols(dev.h, ptr(Kuf), nu, n, ld, None, ptr(ginv), 1.0, ptr(T), ld, st), "gpx_scale_rows_cols")
+        check(lib.gpx_trsm(dev.h, ptr(S), nu, uu.ldu, ptr(T), n, ld, st), "gpx_trsm")
+        P = dev.zeros(max(n, 1), ld)
+        check(lib.gpx_diag_update(dev.h, ptr(P), n, ld, 0.0, ptr(ginv), 0.0, st), "gpx_diag_update")
+        check(lib.gpx_dgemm_tn_sub(dev.h, ptr(T), ld, ptr(T), ld, ptr(P), ld, n, n, nu, 0, st), "gpx_dgemm_tn_sub")
+        self.P = P
+        self.jitter = 0.0
+
+    def covariance(self) -> np.ndarray:
+        return self._cov[: self.n, : self.n].cpu().numpy()
+
+    def precision(self) -> np.ndarray:
+        return self.P[: self.n, : self.n].cpu().numpy()
+
+    def cross_gram(self, X: PointSet):
+        dev, D = self.dev, self.design
+        Kx = dev.zeros(max(self.n, 1), X.ld)
+        check(lib.gpx_gram(dev.h, ptr(D.X), self.n, D.ld, ptr(X.X), X.n, X.ld, ptr(Kx), X.ld, 0, None, 0.0, dev.stream), "gpx_gram")
+        return Kx
+
+    def apply_precision(self, B, ncols: int, ldb: int):
+        """Z = P B for a device matrix B (n x ldb); P is symmetric, so it is its own K-major operand."""
+        dev = self.dev
+        Z = dev.zeros(max(self.n, 1), ldb)
+        check(lib.gpx_dgemm_tn_sub(dev.h, ptr(self.P), self.ld, ptr(B), ldb, ptr(Z), ldb, self.n, ncols, self.n, 0, dev.stream),
+              "gpx_dgemm_tn_sub")
+        check(lib.gpx_scale_rows_cols(dev.h, ptr(Z), self.n, ncols, ldb, None, None, -1.0, ptr(Z), ldb, dev.stream),
+              "gpx_scale_rows_cols")
+        return Z
+
+    def solve_gram(self, X: PointSet, W=None, want_var=True):
+        """(K(D,X), var) with var = k(x,x) - k^T P k  (gp.py:246-256 with the FITC precision)."""
+        dev = self.dev
+        Kx = self.cross_gram(X)
+        var = None
+        if want_var:
+            Z = self.apply_precision(Kx, X.n, X.ld)
+            var = dev.zeros(X.ld)
+            check(lib.gpx_prior_diag(dev.h, ptr(X.X), X.n, X.ld, ptr(var), dev.stream), "gpx_prior_diag")
+            check(lib.gpx_coldot(dev.h, ptr(Kx), ptr(Z), self.n, X.n, X.ld, ptr(var), ptr(var), dev.stream), "gpx_coldot")
+        return Kx, var
+
+    def solve_vector(self, y: np.ndarray) -> np.ndarray:
+        """P y  (GP.train coefficients, gp.py:101)."""
+        dev = self.dev
+        B = dev.zeros(max(self.n, 1), 2)
+        B[: self.n, 0] = dev.upload(np.asarray(y, dtype=np.float64))
+        return self.apply_precision(B, 1, 2)[: self.n, 0].cpu().numpy()
+
+    def logdet(self) -> float:
+        """log det(Q + G) through a Cholesky factor of the dense FITC covariance (np.linalg.slogdet, gp.py:432)."""
+        dev, n = self.dev, self.n
+        C = self._cov.clone()
+        info = dev.zeros(1, dtype=torch.int32)
+        check(lib.gpx_potrf(dev.h, ptr(C), n, self.ld, ptr(info), dev.stream), "gpx_potrf")
+        if int(info.item()):
+            raise GpxError("FITC covariance is not positive definite")
+        out = dev.zeros(1)
+        check(lib.gpx_logdet_chol(dev.h, ptr(C), n, self.ld, ptr(out), dev.stream), "gpx_logdet_chol")
+        return float(out.item())
+
+    def quad_form(self, y: np.ndarray) -> float:
+        return float(np.dot(np.asarray(y, dtype=np.float64), self.solve_vector(y)))
 
 
 class GreedyIVAREngine(_Pivoting):

@@ -185,9 +185,9 @@ int gpx_argreduce(gpx_handle h, const double* v, const double* weights, const ui
 /* Deterministic sum of n doubles (fixed tree order). */
 int gpx_sum(gpx_handle h, const double* v, int64_t n, double* out, void* stream);
 
-/* Ring geometry of the IVAR contraction kernel (A/B measurements; results are identical): 0 = 32-row chunks x 3 stages,
- * all warps in step; 1 / 2 = 16-row chunks x 6 stages with the second warp group held 1 / 2 chunks behind the first so
- * that one group's per-tile exp prologue overlaps the other's DMMA stream. */
+/* Operand pipeline of the IVAR contraction kernel (A/B measurements; results are bit-identical): 0 = 32-row chunks x 3
+ * stages fed by one bulk copy per operand row; 1 = the same ring fed by one 2-D tensor-map TMA load per operand chunk;
+ * 2 = 24-row chunks x 4 stages, two chunks ahead, tensor-map loads. */
 int gpx_set_ivar_ring(gpx_handle h, int ring);
 
 /* Workspace (doubles) gpx_score_ivar needs for C candidates. */
@@ -343,10 +343,38 @@ int gpx_se_dgram(gpx_handle h, const double* X, int64_t nx, int64_t ldx, const d
                  double* out, int64_t ld, void* stream);
 
 /* Posterior-variance gradient with respect to the design coordinates (GP.evaluateVarianceDerivative, gp.py:282-341):
- *     out[(j*d+k)*ldx + m] = 2 At[j,m] ( D(x_m, p_j)[k] - Qneg[(j*d+k), m] ),   At = P K(D, X) (n x ldx),
- *     Qneg = -(dK/dp)^T At from gpx_se_dgram + gpx_dgemm_tn_sub.  P: design points, X: query points. */
+ *     out[(j*d+k)*ldx + m] = 2 At[j,m] ( D(x_m, p_j)[k] - Qneg[(j*d+k), m] ) - At[j,m]^2 diag[j*d+k],
+ *     At = P K(D, X) (n x ldx), Qneg = -(dK/dp)^T At from gpx_se_dgram + gpx_dgemm_tn_sub.  P: design points, X: query
+ *     points.  diag (nullable): d noise(p_j)/d p_j[k] of a heteroscedastic noise function (gp.py:314-318), the caller
+ *     having added the same numbers to the derivative Gram before forming Qneg. */
 int gpx_se_var_grad(gpx_handle h, const double* P, int64_t n, int64_t ldp, const double* X, int64_t M, int64_t ldx,
-                    const double* At, const double* Qneg, double* out, void* stream);
+                    const double* At, const double* Qneg, const double* diag, double* out, void* stream);
+
+/* f3  Hyper-parameter gradient of the marginal log-likelihood, squared-exponential kernels (gp.py:447-468 with
+ *     kernels.py:125-144):  out[q] = 1/2 tr((alpha alpha^T - P) dK/dtheta_q), theta = cl_0..cl_{d-1}, signalSize, noise
+ *     (d + 2 entries; the noise entry is the bare trace -- the caller applies the reference's 2*noise factor).
+ *     P: precision (n x ldp), alpha = P y.  workspace: gpx_se_loglike_grad_workspace(n, d) doubles. */
+int64_t gpx_se_loglike_grad_workspace(int64_t n, int d);
+int gpx_se_loglike_grad(gpx_handle h, const double* X, int64_t n, int64_t ldx, const double* P, int64_t ldp,
+                        const double* alpha, double* workspace, double* out, void* stream);
+
+/* f4  Matrix-free Gram x vector: out[i] = sum_j k(X[i], Y[j]) b[j]   (covTimesV, gp_kernel_utilities.py:107-142: the
+ *     linear operator inside the Nystrom eigen-solver).  workspace: gpx_gram_matvec_workspace(n) doubles. */
+int64_t gpx_gram_matvec_workspace(int64_t n);
+int gpx_gram_matvec(gpx_handle h, const double* X, int64_t n, int64_t ldx, const double* Y, int64_t m, int64_t ldy,
+                    const double* b, double* workspace, double* out, void* stream);
+
+/* Dense helpers of the FITC (sparse-GP) precision, gp_kernel_utilities.py:70-104 / gp.py:182-208:
+ *     gpx_scale_rows_cols  out[i,j] = scale * A[i,j] * (r ? r[i] : 1) * (c ? c[j] : 1)
+ *     gpx_diag_update      A[i,i]   = scale * A[i,i] + (d ? d[i] : shift)
+ *     gpx_axpby            y        = alpha x + beta y
+ *     gpx_coldot           out[j]   = (base ? base[j] : 0) - sum_i A[i,j] B[i,j]      (k^T P k with P k materialised) */
+int gpx_scale_rows_cols(gpx_handle h, const double* A, int64_t rows, int64_t cols, int64_t lda, const double* r,
+                        const double* c, double scale, double* out, int64_t ldo, void* stream);
+int gpx_diag_update(gpx_handle h, double* A, int64_t n, int64_t ld, double scale, const double* d, double shift, void* stream);
+int gpx_axpby(gpx_handle h, int64_t n, double alpha, const double* x, double beta, double* y, void* stream);
+int gpx_coldot(gpx_handle h, const double* A, const double* B, int64_t n, int64_t ncols, int64_t ld, const double* base,
+               double* out, void* stream);
 
 /* out[r] = scale * sum_c A[r,c], fixed order (row mean of the gradient matrix = costFunctionGP_IVAR.derivative,
  * experimentalDesign.py:166-169). */
