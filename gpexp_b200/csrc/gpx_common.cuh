@@ -55,7 +55,7 @@ struct gpx_context {
 };
 
 #ifndef GPX_DEFAULT_IVAR_RING
-#define GPX_DEFAULT_IVAR_RING 0
+#define GPX_DEFAULT_IVAR_RING 1
 #endif
 
 #define GPX_RED_SLOTS 2048

@@ -39,14 +39,15 @@
 
 namespace {
 
-// expanded-form covariance with the table exp; tab already carries the signal variance
+// expanded-form covariance with the table exp.  The table carries the signal variance AND the sign the accumulators
+// need (tab[j] = -signal * 2^(j/256)), so these return -k(x,y) without a negation per element.
 template <int FAM>
-__device__ __forceinline__ double kexpand_tab(double e, const KParams& kp, const double* __restrict__ tab) {
+__device__ __forceinline__ double neg_kexpand_tab(double e, const KParams& kp, const double* __restrict__ ntab) {
     if (FAM == GPX_MATERN32) {
         const double t = kp.c0 * sqrt(fmax(e, 0.0));
-        return (1.0 + t) * gpx_exp_tab(-t, tab);
+        return (1.0 + t) * gpx_exp_tab(-t, ntab);
     }
-    return gpx_exp_tab(e, tab);
+    return gpx_exp_tab(e, ntab);
 }
 
 constexpr int BN = 128;
@@ -131,7 +132,7 @@ __device__ __forceinline__ void mma_tile(double (&acc)[4][8][2], const double (&
 
 // Difference-form covariance of the warp's 32x64 accumulator block from coordinates staged in shared memory:
 // sa / sb point at row 0 of the staged A / B coordinates, offset to this thread's first i / j (see the index map).
-// On exit acc = -k(i,j).
+// `tab` is the NEGATED exp table (-signal * 2^(j/256)); on exit acc = -k(i,j).
 template <int FAM, int LDA_, int LDB_>
 __device__ __forceinline__ void diff_prologue(double (&acc)[4][8][2], const KParams& kp, const double* __restrict__ sa,
                                               const double* __restrict__ sb, const double* __restrict__ tab) {
@@ -168,7 +169,7 @@ __device__ __forceinline__ void diff_prologue(double (&acc)[4][8][2], const KPar
 #pragma unroll
         for (int u = 0; u < 8; ++u)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) acc[t][u][e] = -kfinish_tab<FAM>(acc[t][u][e], kp, tab);
+            for (int e = 0; e < 2; ++e) acc[t][u][e] = kfinish_tab<FAM>(acc[t][u][e], kp, tab);  // tab is negated: -k
 }
 
 // squares of the warp's accumulator block summed over its 32 rows: butterfly reduce-scatter over the 8 lanes that
@@ -179,17 +180,26 @@ __device__ __forceinline__ void column_squares(const double (&acc)[4][8][2], boo
     double p[8][2];
 #pragma unroll
     for (int u = 0; u < 8; ++u) p[u][0] = p[u][1] = 0.0;
+    if (full) {  // every row of the tile is a real integration point: no masking
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const int64_t i = i_first + (t >> 1) * 16 + g4 * 2 + (t & 1);
-        const bool ok = full || (i < I);
+        for (int t = 0; t < 4; ++t)
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+            for (int u = 0; u < 8; ++u)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const double v = ok ? acc[t][u][e] : 0.0;
-                p[u][e] = fma(v, v, p[u][e]);
-            }
+                for (int e = 0; e < 2; ++e) p[u][e] = fma(acc[t][u][e], acc[t][u][e], p[u][e]);
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int64_t i = i_first + (t >> 1) * 16 + g4 * 2 + (t & 1);
+            const bool ok = i < I;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double v = ok ? acc[t][u][e] : 0.0;
+                    p[u][e] = fma(v, v, p[u][e]);
+                }
+        }
     }
     const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
     double h[4][2], q[2][2];
@@ -250,7 +260,7 @@ __global__ void __launch_bounds__(Cfg::NT, 2)
     const int G = ntiles * T;
 
     if (PRO != PRO_NONE) {
-        for (int i = tid; i < 256; i += NT) s_tab[i] = kp.signal * gpx_exp2_tab[i];
+        for (int i = tid; i < 256; i += NT) s_tab[i] = -kp.signal * gpx_exp2_tab[i];
     }
 
     // ---- chunk loader (cp.async ring, 3 chunks in flight) ------------------------------------------
@@ -381,7 +391,7 @@ __global__ void __launch_bounds__(Cfg::NT, 2)
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) acc[t][u][e] = -kexpand_tab<FAM>(acc[t][u][e], kp, s_tab);
+                    for (int e = 0; e < 2; ++e) acc[t][u][e] = neg_kexpand_tab<FAM>(acc[t][u][e], kp, s_tab);
         }
 
         if (ch == T - 1) {
@@ -558,7 +568,7 @@ __global__ void __launch_bounds__(256, 1) ivar_ws_kernel(const __grid_constant__
     double* s_red = smem + NST * RING::STAGE;
     uint64_t* full = reinterpret_cast<uint64_t*>(s_red + 4 * BN);
     uint64_t* empty = full + NST;
-    double* s_tab = reinterpret_cast<double*>(empty + NST);          // signal * 2^(j/256)
+    double* s_tab = reinterpret_cast<double*>(empty + NST);          // -signal * 2^(j/256)
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -592,7 +602,7 @@ __global__ void __launch_bounds__(256, 1) ivar_ws_kernel(const __grid_constant__
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if (tid < 256) s_tab[tid] = kp.signal * gpx_exp2_tab[tid];
+    if (tid < 256) s_tab[tid] = -kp.signal * gpx_exp2_tab[tid];
     __syncthreads();
 
     double rs[2] = {0.0, 0.0};
@@ -716,7 +726,7 @@ __global__ void __launch_bounds__(256, 1) ivar_ws_kernel(const __grid_constant__
 #pragma unroll
                         for (int u = 0; u < 8; ++u)
 #pragma unroll
-                            for (int e = 0; e < 2; ++e) acc[t][u][e] = -kexpand_tab<FAM>(acc[t][u][e], kp, s_tab);
+                            for (int e = 0; e < 2; ++e) acc[t][u][e] = neg_kexpand_tab<FAM>(acc[t][u][e], kp, s_tab);
                 }
             }
             // this warp is done with stage s (all its LDS results have been consumed)

@@ -1,5 +1,10 @@
-"""Gram-matrix builder (mirrors gpExp/gp_kernel_utilities.py:34-68) on the fused CUDA Gram kernel (K1).
-The FITC / Nystrom helpers of the reference file are approximation features off the greedy path."""
+"""Gram-matrix builders (gpExp/gp_kernel_utilities.py) on the CUDA library:
+
+    calculateCovarianceMatrix          :34-68    fused distance + kernel Gram (K1)
+    calculateCovarianceMatrixFITC      :70-104   FITC covariance / precision through two Cholesky factors
+    covTimesV                          :107-142  matrix-free Gram x vector (the operator of the Nystrom eigen-solver)
+    calculateKernelBasisFunctionsMC    :144-194  eigsh (ARPACK, on the host as in the reference) over the device operator
+"""
 import numpy as np
 
 from ._lib import check, lib
@@ -28,3 +33,59 @@ def calculateCovarianceMatrix(kernel, points, nugget=0.0):
                        0.0 if nug_vec is not None else float(nugget), dev.stream), "gpx_gram")
     # gpx_gram writes out[i, j] = k(X[i], Y[j]); the reference's [j, i] = k(x_i, x_j) is its transpose
     return out[:size_of_mat, :size_of_mat].t().contiguous().cpu().numpy()
+
+
+def calculateCovarianceMatrixFITC(kernel, nodes, nugget, fitc, returnCov=False):
+    """FITC precision (and covariance) of `nodes` (gp_kernel_utilities.py:70-104).  `fitc` is either the fraction of nodes
+    to draw as inducing points (np.random.permutation, as the reference) or the inducing points themselves."""
+    from .engine import FitcFactor
+    if isinstance(fitc, float):
+        count = int(np.floor(len(nodes) * fitc))
+        snodes = np.array(nodes[np.random.permutation(len(nodes))[0:count]], dtype=float)
+    else:
+        snodes = fitc
+    dev = kernel._bind()
+    f = FitcFactor(dev, dev.points(nodes), dev.points(np.asarray(snodes, dtype=np.float64)), _nugget_arg(nugget))
+    precMat = f.precision()
+    if returnCov is False:
+        return (precMat, snodes) if fitc is not False else precMat
+    covmat = f.covariance().T.copy()
+    return (covmat, precMat, snodes) if fitc is not False else (covmat, precMat)
+
+
+class _GramOperator:
+    """v -> K(mcPoints, mcPoints) v without the matrix: coordinates stay resident, one fused kernel per product."""
+
+    def __init__(self, kernel, mcPoints):
+        self.kernel = kernel
+        self.dev = kernel._bind()
+        self.P = self.dev.points(mcPoints)
+        self.ws = self.dev.zeros(max(int(lib.gpx_gram_matvec_workspace(self.P.n)), 1))
+        self.out = self.dev.zeros(self.P.ld)
+
+    def __call__(self, b):
+        dev, P = self.dev, self.P
+        self.kernel._bind(dev)
+        bd = dev.upload(np.ascontiguousarray(b, dtype=np.float64).ravel())
+        check(lib.gpx_gram_matvec(dev.h, ptr(P.X), P.n, P.ld, ptr(P.X), P.n, P.ld, ptr(bd), ptr(self.ws), ptr(self.out),
+                                  dev.stream), "gpx_gram_matvec")
+        return self.out[: P.n].cpu().numpy()
+
+
+def covTimesV(b, kernel, mcPoints):
+    """out[i] = sum_j kernel(mcPoints[j], mcPoints[i]) b[j]  (gp_kernel_utilities.py:107-142; the reference forks one
+    process per core and evaluates one kernel row per Python iteration)."""
+    return _GramOperator(kernel, mcPoints)(b).reshape(np.shape(b))
+
+
+def calculateKernelBasisFunctionsMC(kernel, numBasis, mcPoints):
+    """Leading eigenpairs of the kernel's integral operator by Monte Carlo + Nystrom (gp_kernel_utilities.py:144-194):
+    eigsh over the matrix-free Gram operator, eigenvalues / nMC in descending order, eigenvectors * sqrt(nMC)."""
+    from scipy.sparse.linalg import LinearOperator, eigsh
+    nMC = mcPoints.shape[0]
+    k = int(min(numBasis, nMC))
+    op = _GramOperator(kernel, mcPoints)
+    A = LinearOperator((nMC, nMC), matvec=op, dtype=float)
+    eigv, eigve = eigsh(A, k=k, maxiter=10 * k)
+    eigv, eigve = eigv[::-1], eigve[:, ::-1]
+    return eigv / float(nMC), eigve * np.sqrt(float(nMC))

@@ -493,3 +493,79 @@ def fast_variance_derivative(kern, design, newpt, noise):
             q = a @ dc[:, k]                              # sum_c dc[c] a[m,c]
             out[j * d + k] = -2.0 * a[:, j] * t_j[:, k] + 2.0 * a[:, j] * q
     return out
+
+
+# --------------------------------------------------------------------------
+# SURVEY.md 8(f) rows 2-4 (round 2): heteroscedastic variance derivative, log-likelihood gradient, FITC, Gram x vector
+# --------------------------------------------------------------------------
+def ref_variance_derivative_hetero(kern, design, newpt, nugget_vec, noise_deriv):
+    """gp.py:282-341 with a noise function: the loops of the reference, line for line, for SE kernels.
+    nugget_vec = noiseFunc(design) (the per-point nugget the Gram was built with), noise_deriv = noiseFunc.deriv(design).
+    The `np.linalg.norm(p - newpt) < 1e-10` adjustment (:317-319) is the norm of the whole difference matrix and is kept."""
+    n, d = design.shape
+    m = newpt.shape[0]
+    prec = np.linalg.pinv(kern.gram(design, design) + np.diag(nugget_vec))
+    deriv_cov = np.zeros((n, n, d))
+    tot = np.zeros((m, n))
+    deriv_total = []
+    for zz in range(n):
+        p = design[zz:zz + 1]
+        ind = np.array([np.linalg.norm(pp - p) < 1e-10 for pp in design])
+        deriv_cov[zz] = se_derivative(kern, design, p)
+        tot[:, zz] = kern.evaluate(np.tile(p, (m, 1)), newpt)
+        deriv_total.append(-se_derivative(kern, newpt, p))
+        deriv_cov[zz] += np.tile(ind.reshape(n, 1), d) * noise_deriv
+        if np.linalg.norm(p - newpt) < 1e-10:
+            raise NotImplementedError("degenerate query: every evaluation point on a design point")
+    a = tot @ prec
+    out1 = np.zeros((n * d, m))
+    out2 = np.zeros((n * d, m))
+    for jj in range(n):
+        for kk in range(d):
+            out1[jj * d + kk] = 2.0 * a[:, jj] * deriv_total[jj][:, kk]
+            ds = np.zeros((n, n))
+            ds[jj, :] = deriv_cov[:, jj, kk]
+            ds[:, jj] = deriv_cov[:, jj, kk]
+            out2[jj * d + kk] = -np.sum((a @ ds) * a, axis=1)
+    return -(out1 + out2)
+
+
+def fast_loglike_gradient(kern, pts, evals, noise):
+    """gp.py:447-468 with kernels.py:125-144: d loglike / d theta = 1/2 tr((alpha alpha^T - K^-1) dK/dtheta) for
+    theta = cl_0..cl_{d-1}, signalSize, and 'noise' (the trace times 2*noise, gp.py:463-464).  Returns a dict keyed like the
+    reference's.  PARITY UNPINNED: the reference indexes `x1[:, direction]` with a float (kernels.py:140-142) and raises
+    IndexError under numpy >= 1.12, so no golden vector can be produced; this is the expression the reference states, and
+    the tests additionally check it against central finite differences of the (golden-pinned) log-likelihood value."""
+    assert kern.family == SE
+    n, d = pts.shape
+    kmat = kern.gram(pts, pts)
+    cov = kmat + noise * np.eye(n)
+    prec = np.linalg.inv(cov)
+    alpha = prec @ evals
+    term = np.outer(alpha, alpha) - prec
+    out = {}
+    for q in range(d):
+        diff2 = (pts[:, None, q] - pts[None, :, q]) ** 2.0
+        out["cl%d" % q] = 0.5 * float(np.sum(term * kmat * diff2 / kern.cl[q] ** 3.0))
+    out["signalSize"] = 0.5 * float(np.sum(term * kmat / kern.signal))
+    out["noise"] = 0.5 * float(np.trace(term)) * noise * 2.0
+    return out
+
+
+def ref_fitc(kern, nodes, inducing, noise):
+    """gp.py:193-208 / gp_kernel_utilities.py:81-97: FITC covariance Q + G and its Woodbury precision, with the reference's
+    pinv / inv calls.  Returns (covariance, precision)."""
+    quu = ref_covariance_matrix(kern, inducing, noise)
+    inv_quu = np.linalg.pinv(quu)
+    kuf = np.array([kern.evaluate(np.tile(s[None, :], (len(nodes), 1)), nodes) for s in inducing])
+    q = kuf.T @ inv_quu @ kuf
+    kff = ref_covariance_matrix(kern, nodes, noise)
+    g = np.diag(kff - q)
+    inv_g = np.diag(1.0 / (g + 1e-12))
+    prec = inv_g - inv_g @ kuf.T @ np.linalg.inv(quu + kuf @ inv_g @ kuf.T) @ kuf @ inv_g
+    return q + np.diag(g), prec
+
+
+def ref_cov_times_v(kern, pts, b):
+    """gp_kernel_utilities.py:107-142: out[i] = kernel.evaluate(pts, pts[i]) . b, one row per iteration."""
+    return np.array([np.dot(kern.evaluate(pts, np.tile(pts[i:i + 1], (len(pts), 1))), b) for i in range(len(pts))])

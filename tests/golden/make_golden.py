@@ -281,7 +281,7 @@ def main():
     only = sys.argv[1:]
     for fname, gen in [("kernels.npz", gen_kernels), ("gram.npz", gen_gram), ("gp.npz", gen_gp),
                        ("greedy_var.npz", gen_greedy_var), ("greedy_ivar.npz", gen_greedy_ivar),
-                       ("greedy_mi.npz", gen_greedy_mi), ("next.npz", gen_next), ("cfg1.npz", gen_cfg1)]:
+                       ("greedy_mi.npz", gen_greedy_mi), ("next.npz", gen_next), ("cfg1.npz", gen_cfg1), ("next2.npz", gen_next2)]:
         if only and fname not in only:
             continue
         out = {}
@@ -338,6 +338,83 @@ def gen_next(out):
     out["next/slsqp/end_greedy"] = end2
     out["next/slsqp/cost_start"] = np.float64(cf.evaluate(start))
     out["next/slsqp/cost_end"] = np.float64(cf.evaluate(end))
+
+
+
+from make_golden_shared import QuadNoise  # noqa: E402  (same directory)
+
+
+def gen_next2(out):
+    """SURVEY.md 8(f) rows 2 and 4 from the unmodified reference: heteroscedastic variance derivative (gp.py:282-341,
+    noiseFunc branch) and IVAR gradient, the batch-greedy optimiser wrapper (experimentalDesign.py:694-751), FITC
+    covariance / precision / prediction (gp.py:182-208, gp_kernel_utilities.py:70-104), covTimesV and the Nystrom
+    eigenvalues (gp_kernel_utilities.py:107-194)."""
+    rng = np.random.default_rng(108)
+    nf = QuadNoise()
+    for name, n, m in [("se_ard_2d_wide", 8, 300), ("se_iso_1d", 5, 200)]:
+        kern, d = mk_kernel(name)
+        design = sample(rng, name, n, d)
+        mc = sample(rng, name, m, d)
+        gp = rgp.GP(kern, 1e-6)
+        gp.addNodesAndComputeCovariance(design, noiseIn=nf(design))
+        cf = red.costFunctionGP_IVAR(gp, n, Space(d, None, None, noise=nf), mcPoints=mc)
+        out[f"next2/hetero/{name}/design"] = design
+        out[f"next2/hetero/{name}/mc"] = mc
+        out[f"next2/hetero/{name}/var_deriv"] = gp.evaluateVarianceDerivative(mc[:48], noiseFunc=nf)
+        out[f"next2/hetero/{name}/ivar_deriv"] = cf.derivative(design)
+        out[f"next2/hetero/{name}/ivar_cost"] = np.float64(cf.evaluate(design))
+    # batch-greedy continuous design: 2 + 2 points, each batch = greedy max-variance start + SLSQP polish
+    kern, d = mk_kernel("se_ard_2d_wide")
+    mc = sample(rng, "se", 500, d)
+    srng = np.random.default_rng(7)
+    dens = lambda p: np.all(np.abs(p) <= 1.0, axis=1).astype(float)  # noqa: E731
+    space = Space(d, lambda s: srng.uniform(-1, 1, s), dens, noise=None)
+    cf = red.costFunctionGP_IVAR(rgp.GP(kern, 1e-6), 2, space, mcPoints=mc)
+    exp = red.ExperimentalDesignGreedyWithDerivatives(cf, 4, 2, d)
+    pts = quiet(exp.begin)
+    out["next2/batch/mc"] = mc
+    out["next2/batch/points"] = pts
+    out["next2/batch/cost"] = np.float64(red.costFunctionGP_IVAR(rgp.GP(kern, 1e-6), 4, space, mcPoints=mc).evaluate(pts))
+    # FITC sparse GP
+    for name, noise in [("se_ard_2d_wide", 1e-4), ("matern_5d", 1e-3)]:
+        kern, d = mk_kernel(name)
+        nodes = sample(rng, name, 30, d)
+        query = sample(rng, name, 120, d)
+        fvals = np.sin(nodes.sum(axis=1))
+        np.random.seed(11)
+        gp = rgp.GP(kern, noise, FITC=0.5)
+        gp.train(nodes, fvals)
+        out[f"next2/fitc/{name}/nodes"] = nodes
+        out[f"next2/fitc/{name}/query"] = query
+        out[f"next2/fitc/{name}/fvals"] = fvals
+        out[f"next2/fitc/{name}/noise"] = np.float64(noise)
+        out[f"next2/fitc/{name}/inducing"] = gp.fitcnodes
+        out[f"next2/fitc/{name}/cov"] = gp.covarianceMatrix
+        out[f"next2/fitc/{name}/prec"] = gp.precisionMatrix
+        out[f"next2/fitc/{name}/coeff"] = gp.coeff
+        out[f"next2/fitc/{name}/var"] = gp.evaluateVariance(query, parallel=0)
+        mean, absvar = gp.evaluate(query, compvar=1)
+        out[f"next2/fitc/{name}/mean"] = mean
+        out[f"next2/fitc/{name}/absvar"] = absvar
+        np.random.seed(11)
+        out[f"next2/fitc/{name}/loglike"] = np.float64(rgp.GP(kern, noise, FITC=0.5).computeLogLike(nodes, fvals))
+        covmat, precmat, sn = rku.calculateCovarianceMatrixFITC(kern, nodes, noise, gp.fitcnodes, returnCov=True)
+        out[f"next2/fitc/{name}/util_cov"] = covmat
+        out[f"next2/fitc/{name}/util_prec"] = precmat
+    # matrix-free Gram x vector and the Nystrom eigenvalues
+    for name in ["se_ard_2d_wide", "matern_5d", "mehler_3d_b"]:
+        kern, d = mk_kernel(name)
+        pts = sample(rng, name, 260, d)
+        b = rng.standard_normal(260)
+        out[f"next2/matvec/{name}/pts"] = pts
+        out[f"next2/matvec/{name}/b"] = b
+        out[f"next2/matvec/{name}/Kb"] = np.asarray(quiet(rku.covTimesV, b, kern, pts)).reshape(-1)
+    kern, d = mk_kernel("se_ard_2d_wide")
+    pts = sample(rng, "se", 200, d)
+    eigv, eigve = quiet(rku.calculateKernelBasisFunctionsMC, kern, 6, pts)
+    out["next2/nystrom/pts"] = pts
+    out["next2/nystrom/eigv"] = eigv
+    out["next2/nystrom/eigve"] = eigve
 
 
 if __name__ == "__main__":

@@ -104,9 +104,53 @@ def test_api_surface_matches_reference_names():
     g = gp.GP(k, 1e-6)
     assert g.noise == 1e-6 and g.kernel is not k and g.pts is None and g.covarianceMatrix is None
     import gpexp_b200
-    gpexp_b200.install_as_gpExp()
+    gpexp_b200.install_as_gpExp(False)  # standalone registration: the package's own modules answer to `gpExp`
     import gpExp.experimentalDesign as red
     assert red.costFunctionGP_IVAR is ed.costFunctionGP_IVAR
+    for name in [m for m in list(__import__("sys").modules) if m == "gpExp" or m.startswith("gpExp.")]:
+        del __import__("sys").modules[name]
+
+
+def test_patch_reference_rebinds_only_hot_methods():
+    """install_as_gpExp(path) with the reference importable keeps the reference's classes, constructors and optimiser loops
+    and rebinds only the device methods (do not re-type reference host code)."""
+    path = next((p for p in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference")
+                 if os.path.isdir(os.path.join(p, "gpExp"))), None)
+    if path is None:
+        pytest.skip("no reference package available")
+    import sys
+    import gpexp_b200
+    from gpexp_b200 import experimentalDesign as ed, gp, gp_kernel_utilities as gku, kernels
+    ref = gpexp_b200.install_as_gpExp(path)
+    try:
+        import gpExp.experimentalDesign as red
+        import gpExp.gp as rgp
+        import gpExp.gp_kernel_utilities as rku
+        import gpExp.kernels as rk
+        assert ref.__gpexp_b200_patched__ and os.path.realpath(ref.__file__).startswith(os.path.realpath(path))
+        for cls, methods in kernels.DEVICE_METHODS.items():
+            for name, fn in methods.items():
+                assert getattr(getattr(rk, cls), name) is fn
+        assert rk.KernelSquaredExponential.__init__.__module__ == "gpExp.kernels"
+        assert rk.KernelMehlerND.updateHyperParameters.__module__ == "gpExp.kernels"
+        for name, fn in gp.DEVICE_METHODS.items():
+            assert getattr(rgp.GP, name) is fn
+        assert rgp.GP.__init__.__module__ == "gpExp.gp" and rgp.GP.findOptParamsLogLike.__module__ == "gpExp.gp"
+        assert isinstance(rgp.GP.__dict__["covarianceMatrix"], property)
+        assert rku.calculateCovarianceMatrix is gku.calculateCovarianceMatrix is rgp.calculateCovarianceMatrix
+        assert red.costFunctionGP_IVAR.evaluate is ed.costFunctionGP_IVAR.evaluate
+        assert red.costFunctionGP_IVAR.__init__.__module__ == "gpExp.experimentalDesign"
+        assert red.performGreedyMIExperimentalDesign is ed.performGreedyMIExperimentalDesign
+        for name in ("ExperimentalDesignDerivative", "ExperimentalDesignNoDerivative", "ExperimentalDesignGreedyWithDerivatives"):
+            assert getattr(red, name).begin.__module__ == "gpExp.experimentalDesign"
+        # constructing reference objects works without a device; the hot call then fails loudly (no CPU fallback)
+        k = rk.KernelSquaredExponential([0.3], 2.0, 3)
+        assert k.hyperParam['cl2'] == 0.3 and k._gpx_spec()[0] == 0
+        g = rgp.GP(k, 1e-6)
+        assert g.covarianceMatrix is None and g._pending is None
+    finally:
+        for name in [m for m in list(sys.modules) if m == "gpExp" or m.startswith("gpExp.")]:
+            del sys.modules[name]
 
 
 def test_host_logic_splits_and_scales():

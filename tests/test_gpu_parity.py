@@ -8,8 +8,12 @@ where the reference's own pinv round-off is larger (cond * eps, SURVEY.md sectio
 """
 import ctypes as C
 
+import os
+
 import numpy as np
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 from oracle import gpexp_oracle as orc
 from tests.cases import KERNEL_NAMES, product_kernel, spec
@@ -198,7 +202,7 @@ def test_greedy_mi_golden(gx, golden):
         pts = gx.ed.performGreedyMIExperimentalDesign(cf, len(idx), start=start)
         assert [int(i) for i in cf.lastIndices] == [int(i) for i in idx], (ci, name)
         assert np.array_equal(pts, pool[idx])
-        eng = cf._new_engine(len(idx))
+        eng = gx.ed._mi_new_engine(cf, len(idx))
         eng.score_trace = []
         eng.run(len(idx), start=start)
         for s, sc in enumerate(eng.score_trace):
@@ -656,25 +660,195 @@ def test_ivar_gradient_matches_finite_differences(gx):
         assert abs(fd - g[j, q]) <= 1e-5 * max(abs(fd), 1e-3), (j, q, fd, g[j, q])
 
 
-def test_next_slsqp_polish_golden(gx, golden):
-    """ExperimentalDesignDerivative.begin / beginWithVarGreedy (experimentalDesign.py:379-497): same start design, and
-    the SLSQP polish driven by the device cost + gradient lands on the reference's end design."""
+@pytest.fixture(scope="module")
+def patched_ref(gx):
+    """The UNMODIFIED reference package from baseline/_ref (copied there by __graft_entry__.build(); git-ignored, shipped to
+    the GPU box), with its hot methods rebound by gpexp_b200.install_as_gpExp: its own constructors and optimiser loops run
+    on the device path."""
+    path = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(path, "gpExp")):
+        pytest.skip("baseline/_ref/gpExp is not present (run __graft_entry__.build() where /root/reference exists)")
+    import gpexp_b200
+    ref = gpexp_b200.install_as_gpExp(path)
+    import importlib
+
+    class R:
+        pass
+    r = R()
+    r.pkg = ref
+    for name in ("kernels", "gp", "gp_kernel_utilities", "experimentalDesign", "approximation"):
+        setattr(r, name, importlib.import_module("gpExp." + name))
+    r.experimentalDesign.VERBOSE = False
+    return r
+
+
+def _quiet(fn, *a, **k):
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def test_patched_reference_keeps_its_own_host_code(gx, patched_ref):
+    r = patched_ref
+    from gpexp_b200 import experimentalDesign as ed, gp, kernels
+    assert os.path.realpath(r.pkg.__file__).startswith(os.path.realpath(os.path.join(ROOT, "baseline", "_ref")))
+    # rebound: the hot methods ...
+    assert r.kernels.Kernel.evaluate is kernels.Kernel.evaluate
+    assert r.gp.GP.evaluateVariance is gp.GP.evaluateVariance and r.gp.GP.train is gp.GP.train
+    assert r.experimentalDesign.costFunctionGP_IVAR.evaluate is ed.costFunctionGP_IVAR.evaluate
+    assert r.experimentalDesign.performGreedyVarExperimentalDesign is ed.performGreedyVarExperimentalDesign
+    # ... and nothing else: constructors and optimiser loops are the reference's own code
+    assert r.kernels.KernelSquaredExponential.__init__.__module__ == "gpExp.kernels"
+    assert r.gp.GP.__init__.__module__ == "gpExp.gp" and r.gp.GP.findOptParamsLogLike.__module__ == "gpExp.gp"
+    assert r.experimentalDesign.ExperimentalDesignDerivative.begin.__module__ == "gpExp.experimentalDesign"
+    assert r.experimentalDesign.costFunctionGP_MI.__init__.__module__ == "gpExp.experimentalDesign"
+
+
+def test_next_slsqp_polish_golden(gx, golden, patched_ref):
+    """ExperimentalDesignDerivative.begin / beginWithVarGreedy (experimentalDesign.py:379-497) -- the REFERENCE's optimiser
+    loop, unmodified, over the device cost + gradient: same start design, and the SLSQP polish lands on the reference's
+    end design."""
+    r = patched_ref
     z = golden("next")
     mc = z["next/slsqp/mc"]
-    k = product_kernel("se_ard_2d_wide")
+    k = r.kernels.KernelSquaredExponential([0.3, 0.45], 1.7, 2)
     dens = lambda p: np.all(np.abs(p) <= 1.0, axis=1).astype(float)  # noqa: E731
-    space = gx.Space(2, None, dens, noise=None)
-    cf = gx.ed.costFunctionGP_IVAR(gx.gp.GP(k, 1e-6), 5, space, mcPoints=mc)
-    exp = gx.ed.ExperimentalDesignDerivative(cf, 5, 2)
-    start = gx.ed.performGreedyVarExperimentalDesign(k, mc, 5, 2)
+    space = r.approximation.Space(2, None, dens, noise=None)
+    cf = r.experimentalDesign.costFunctionGP_IVAR(r.gp.GP(k, 1e-6), 5, space, mcPoints=mc)
+    exp = r.experimentalDesign.ExperimentalDesignDerivative(cf, 5, 2)
+    start = r.experimentalDesign.performGreedyVarExperimentalDesign(k, mc, 5, 2)
     assert np.array_equal(start, z["next/slsqp/start"])
     assert abs(cf.evaluate(start) - float(z["next/slsqp/cost_start"])) <= 1e-9 * float(z["next/slsqp/cost_start"])
-    end = exp.begin([start], list(-np.ones(10)), list(np.ones(10)))
+    end = _quiet(exp.begin, [start], list(-np.ones(10)), list(np.ones(10)))
     # SLSQP stops at acc = 1e-6 on the objective: compare the optimum, and the design to the optimiser's own accuracy
     assert abs(cf.evaluate(end) - float(z["next/slsqp/cost_end"])) <= 1e-6
     assert np.max(np.abs(end - z["next/slsqp/end"])) <= 5e-3
-    end2 = exp.beginWithVarGreedy(None, list(-np.ones(10)), list(np.ones(10)))
+    end2 = _quiet(exp.beginWithVarGreedy, None, list(-np.ones(10)), list(np.ones(10)))
     assert np.max(np.abs(end2 - end)) <= 1e-9
+
+
+def test_next2_batch_greedy_wrapper_golden(gx, golden, patched_ref):
+    """ExperimentalDesignGreedyWithDerivatives.begin (experimentalDesign.py:694-751): the reference's batch-greedy loop
+    (2 + 2 points; each batch = greedy max-variance start + SLSQP polish) driving the device path."""
+    r = patched_ref
+    z = golden("next2")
+    mc = z["next2/batch/mc"]
+    k = r.kernels.KernelSquaredExponential([0.3, 0.45], 1.7, 2)
+    srng = np.random.default_rng(7)
+    dens = lambda p: np.all(np.abs(p) <= 1.0, axis=1).astype(float)  # noqa: E731
+    space = r.approximation.Space(2, lambda s: srng.uniform(-1, 1, s), dens, noise=None)
+    red = r.experimentalDesign
+    cf = red.costFunctionGP_IVAR(r.gp.GP(k, 1e-6), 2, space, mcPoints=mc)
+    pts = _quiet(red.ExperimentalDesignGreedyWithDerivatives(cf, 4, 2, 2).begin)
+    cost = red.costFunctionGP_IVAR(r.gp.GP(k, 1e-6), 4, space, mcPoints=mc).evaluate(pts)
+    assert pts.shape == (4, 2)
+    assert abs(cost - float(z["next2/batch/cost"])) <= 1e-6
+    assert np.max(np.abs(pts - z["next2/batch/points"])) <= 5e-3
+
+
+def test_next2_heteroscedastic_gradient_golden(gx, golden):
+    """f2: GP.evaluateVarianceDerivative(noiseFunc=...) and costFunctionGP_IVAR.derivative with a heteroscedastic noise
+    function (gp.py:282-341, experimentalDesign.py:170-176) against the unmodified reference."""
+    from gpexp_b200 import kernels as K
+    from tests.golden.make_golden_shared import QuadNoise
+    z = golden("next2")
+    nf = QuadNoise()
+    for name, kern in [("se_ard_2d_wide", K.KernelSquaredExponential([0.3, 0.45], 1.7, 2)),
+                       ("se_iso_1d", K.KernelSquaredExponential([0.05], 1.0, 1))]:
+        design, mc = z[f"next2/hetero/{name}/design"], z[f"next2/hetero/{name}/mc"]
+        g = gx.gp.GP(kern, 1e-6)
+        g.addNodesAndComputeCovariance(design, noiseIn=nf(design))
+        got = g.evaluateVarianceDerivative(mc[:48], noiseFunc=nf)
+        ref = z[f"next2/hetero/{name}/var_deriv"]
+        assert got.shape == ref.shape
+        assert np.max(np.abs(got - ref)) <= 1e-9 * np.max(np.abs(ref)), name
+        cf = gx.ed.costFunctionGP_IVAR(gx.gp.GP(kern, 1e-6), len(design), gx.Space(kern.dimension, None, None, noise=nf),
+                                       mcPoints=mc)
+        assert abs(cf.evaluate(design) - float(z[f"next2/hetero/{name}/ivar_cost"])) <= 1e-9 * float(z[f"next2/hetero/{name}/ivar_cost"])
+        gd, rd = cf.derivative(design), z[f"next2/hetero/{name}/ivar_deriv"]
+        assert np.max(np.abs(gd - rd)) <= 1e-9 * np.max(np.abs(rd)), name
+
+
+def test_next2_fitc_golden(gx, golden):
+    """f4: FITC sparse GP (gp.py:182-208, gp_kernel_utilities.py:70-104): same inducing points (np.random.permutation under
+    the same seed), covariance, Woodbury precision, coefficients, mean, variance and log-likelihood of the reference."""
+    z = golden("next2")
+    for name in ["se_ard_2d_wide", "matern_5d"]:
+        k = product_kernel(name)
+        nodes, query, fvals = z[f"next2/fitc/{name}/nodes"], z[f"next2/fitc/{name}/query"], z[f"next2/fitc/{name}/fvals"]
+        noise = float(z[f"next2/fitc/{name}/noise"])
+        np.random.seed(11)
+        g = gx.gp.GP(k, noise, FITC=0.5)
+        g.train(nodes, fvals)
+        assert np.array_equal(g.fitcnodes, z[f"next2/fitc/{name}/inducing"])
+        np.testing.assert_allclose(g.covarianceMatrix, z[f"next2/fitc/{name}/cov"], rtol=1e-10, atol=1e-12)
+        pref = z[f"next2/fitc/{name}/prec"]
+        # the precision carries 1/g ~ 1/noise entries; compare at the scale of the matrix
+        assert np.max(np.abs(g.precisionMatrix - pref)) <= 1e-8 * np.max(np.abs(pref)), name
+        cref = z[f"next2/fitc/{name}/coeff"]
+        assert np.max(np.abs(g.coeff - cref)) <= 1e-7 * np.max(np.abs(cref))
+        var = g.evaluateVariance(query)
+        vref = z[f"next2/fitc/{name}/var"]
+        assert np.max(np.abs(var - vref)) <= 1e-8 * max(1.0, np.max(np.abs(vref))), name
+        mean, absvar = g.evaluate(query, compvar=1)
+        assert np.max(np.abs(mean - z[f"next2/fitc/{name}/mean"])) <= 1e-7 * max(1.0, np.max(np.abs(z[f"next2/fitc/{name}/mean"])))
+        assert np.max(np.abs(absvar - z[f"next2/fitc/{name}/absvar"])) <= 1e-8 * max(1.0, np.max(np.abs(vref)))
+        np.random.seed(11)
+        ll = gx.gp.GP(k, noise, FITC=0.5).computeLogLike(nodes, fvals)
+        assert abs(ll - float(z[f"next2/fitc/{name}/loglike"])) <= 1e-8 * abs(float(z[f"next2/fitc/{name}/loglike"]))
+        cov, prec, sn = gx.gku.calculateCovarianceMatrixFITC(k, nodes, noise, z[f"next2/fitc/{name}/inducing"], returnCov=True)
+        np.testing.assert_allclose(cov, z[f"next2/fitc/{name}/util_cov"], rtol=1e-10, atol=1e-12)
+        assert np.max(np.abs(prec - z[f"next2/fitc/{name}/util_prec"])) <= 1e-8 * np.max(np.abs(pref))
+
+
+def test_next2_gram_matvec_and_nystrom_golden(gx, golden):
+    """f4: covTimesV (gp_kernel_utilities.py:107-142) as one fused Gram x vector kernel, and the Nystrom eigenvalues of
+    calculateKernelBasisFunctionsMC (:144-194) from eigsh over that operator; plus a 20 011-point product against numpy."""
+    z = golden("next2")
+    for name in ["se_ard_2d_wide", "matern_5d", "mehler_3d_b"]:
+        k = product_kernel(name)
+        pts, b, ref = z[f"next2/matvec/{name}/pts"], z[f"next2/matvec/{name}/b"], z[f"next2/matvec/{name}/Kb"]
+        got = gx.gku.covTimesV(b, k, pts)
+        assert got.shape == b.shape and np.max(np.abs(got - ref)) <= 1e-11 * np.max(np.abs(ref)), name
+    k = product_kernel("se_ard_2d_wide")
+    eigv, eigve = gx.gku.calculateKernelBasisFunctionsMC(k, 6, z["next2/nystrom/pts"])
+    rv, rve = z["next2/nystrom/eigv"], z["next2/nystrom/eigve"]
+    assert np.max(np.abs(eigv - rv)) <= 1e-9 * rv[0]
+    for c in range(6):  # eigenvectors are defined up to sign
+        assert min(np.max(np.abs(eigve[:, c] - rve[:, c])), np.max(np.abs(eigve[:, c] + rve[:, c]))) <= 1e-6 * np.max(np.abs(rve[:, c]))
+    rng = np.random.default_rng(9)
+    ks = spec("matern_5d")
+    kk = product_kernel("matern_5d")
+    P = rng.uniform(-1, 1, (20011, 5))
+    v = rng.standard_normal(20011)
+    got = gx.gku.covTimesV(v, kk, P)
+    rows = rng.permutation(20011)[:64]
+    want = ks.gram(P[rows], P) @ v
+    assert np.max(np.abs(got[rows] - want)) <= 1e-11 * np.max(np.abs(want))
+
+
+def test_loglike_gradient_vs_oracle(gx, golden):
+    """f3: loglikeParams(returnDeriv=1) (gp.py:447-468).  The reference's own gradient raises IndexError under current
+    numpy (kernels.py:140-142 indexes with a float), so parity is against the analytic expression restated in the oracle
+    (itself checked against finite differences of the golden-pinned value in tests/test_oracle.py)."""
+    z = golden("next")
+    from gpexp_b200 import kernels as K
+    for name, kern in [("se_ard_2d_wide", K.KernelSquaredExponential([0.3, 0.45], 1.7, 2)),
+                       ("se_ard_10d", K.KernelSquaredExponential(list(np.linspace(0.5, 1.5, 10)), 1.0, 10))]:
+        pts, y = z[f"next/loglike/{name}/nodes"], z[f"next/loglike/{name}/fvals"]
+        for noise in (float(z[f"next/loglike/{name}/noise"]), 1e-3):
+            g = gx.gp.GP(kern, noise)
+            val, grad = g.loglikeParams(pts, y, returnDeriv=1)
+            assert abs(val - orc.fast_loglike(spec(name), pts, y, noise)) <= 1e-9 * abs(val)
+            ref = orc.fast_loglike_gradient(spec(name), pts, y, noise)
+            assert list(grad.keys()) == list(kern.hyperParam.keys()) + ['noise']
+            scale = max(abs(v) for v in ref.values())
+            for key, v in ref.items():
+                assert abs(grad[key] - v) <= 1e-8 * scale, (name, noise, key, grad[key], v)
+    with pytest.raises(AttributeError):
+        gx.gp.GP(product_kernel("matern_5d"), 1e-4).loglikeParams(z["next/loglike/matern_5d/nodes"],
+                                                                   z["next/loglike/matern_5d/fvals"], returnDeriv=1)
 
 
 def test_resident_covariance_mode_equals_contraction_mode(gx):
@@ -954,14 +1128,15 @@ def test_mi_cost_function_caches_the_factorisation(gx, golden):
         keep = idx[:step]
         options = [j for j in range(len(pool)) if j not in keep]
         out = np.array([cf.evaluate(j, keep)[0] for j in options])
-        engines.add(id(cf._eval_engine))
+        engines.add(id(cf._mi_cache["engine"]))
         ref = ref_scores[step][options]
         assert np.max(np.abs(out - ref) / np.abs(ref)) <= 2e-8
         assert options[int(np.argmax(out))] == idx[step]
     assert len(engines) == 1
     # a list that does not extend the previous one replays on the same factorisation
     one = cf.evaluate(options[0], idx[:1])
-    assert abs(one[0] - ref_scores[1][options[0]]) <= 2e-8 * abs(ref_scores[1][options[0]]) and id(cf._eval_engine) in engines
+    assert abs(one[0] - ref_scores[1][options[0]]) <= 2e-8 * abs(ref_scores[1][options[0]]) and id(cf._mi_cache["engine"]) in engines
     np.testing.assert_allclose(cf.invcov, z["gmi/1/invcov"], rtol=0, atol=1e-9 * np.abs(z["gmi/1/invcov"]).max())
     cf.add_candidates(len(pool) - 5, pool[:-5])
-    assert cf._eval_engine is None
+    cf.evaluate(0, [3])
+    assert id(cf._mi_cache["engine"]) not in engines and cf._mi_cache["engine"].V == len(pool) - 5

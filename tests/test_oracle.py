@@ -148,3 +148,81 @@ def test_next_loglike_and_ivar_gradient(golden):
         assert np.max(np.abs(full[:, :64] - ref)) <= tol * np.max(np.abs(ref)), name
         g = z[f"next/grad/{name}/ivar_deriv"]
         assert np.max(np.abs(full.mean(axis=1) - g)) <= tol * np.max(np.abs(g)), name
+
+
+def test_cfg1_full_size_main_variant(golden):
+    """BASELINE configs[0] at full size: the vectorised restatement reproduces the unmodified reference's 20 picks and all
+    20 x 1 000 costs (cl = 0.05, noise 1e-6)."""
+    z = golden("cfg1")
+    cand, mc = z["cfg1/cand"], z["cfg1/mc"]
+    idx, costs = orc.fast_greedy_ivar(orc.KernelSpec.se([float(z["cfg1/main/cl"])], 1.0, 1), cand, mc, 20,
+                                      float(z["cfg1/main/noise"]))
+    assert idx == [int(i) for i in z["cfg1/main/idx"]]
+    ref = z["cfg1/main/costs"]
+    for s in range(20):
+        assert np.max(np.abs(costs[s] - ref[s]) / np.abs(ref[s])) <= 1e-9, s
+
+
+def test_cfg1_stress_variant_first_ten_steps(golden):
+    """demo.py:52-58 values (cl = 0.3, noise 0): picks agree while the reference's own Gram is usable (cond <= 2e6, the
+    first 10 steps); afterwards its cond reaches 3e11 .. 3e17 and the pinv arithmetic is noise."""
+    z = golden("cfg1")
+    cand, mc = z["cfg1/cand"], z["cfg1/mc"]
+    idx, costs = orc.fast_greedy_ivar(orc.KernelSpec.se([0.3], 1.0, 1), cand, mc, 10, 0.0)
+    ref_idx, ref, cond = z["cfg1/stress/idx"], z["cfg1/stress/costs"], z["cfg1/stress/cond"]
+    assert idx == [int(i) for i in ref_idx[:10]]
+    for s in range(10):
+        got, want = costs[s][ref_idx[s]], ref[s, ref_idx[s]]
+        assert abs(got - want) <= max(1e-9, 1e-13 * cond[s]) * abs(want), s
+    assert cond[10] > 1e11
+
+
+def test_next2_hetero_fitc_matvec(golden):
+    z = golden("next2")
+    from tests.golden.make_golden_shared import QuadNoise
+    nf = QuadNoise()
+    for name in ["se_ard_2d_wide", "se_iso_1d"]:
+        ks = spec(name)
+        design, mc = z[f"next2/hetero/{name}/design"], z[f"next2/hetero/{name}/mc"]
+        got = orc.ref_variance_derivative_hetero(ks, design, mc[:48], nf(design), nf.deriv(design))
+        ref = z[f"next2/hetero/{name}/var_deriv"]
+        assert np.max(np.abs(got - ref)) <= 1e-9 * np.max(np.abs(ref))
+    for name in ["se_ard_2d_wide", "matern_5d"]:
+        ks = spec(name)
+        cov, prec = orc.ref_fitc(ks, z[f"next2/fitc/{name}/nodes"], z[f"next2/fitc/{name}/inducing"],
+                                 float(z[f"next2/fitc/{name}/noise"]))
+        np.testing.assert_allclose(cov, z[f"next2/fitc/{name}/cov"], rtol=1e-10, atol=1e-12)
+        ref = z[f"next2/fitc/{name}/prec"]
+        assert np.max(np.abs(prec - ref)) <= 1e-8 * np.max(np.abs(ref))
+    for name in ["se_ard_2d_wide", "matern_5d", "mehler_3d_b"]:
+        ks = spec(name)
+        got = orc.ref_cov_times_v(ks, z[f"next2/matvec/{name}/pts"], z[f"next2/matvec/{name}/b"])
+        ref = z[f"next2/matvec/{name}/Kb"]
+        assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
+
+
+def test_loglike_gradient_matches_finite_differences(golden):
+    """The reference's own gradient raises IndexError (kernels.py:140-142, float index): the analytic expression is checked
+    against central differences of the log-likelihood value, which IS pinned by golden vectors."""
+    z = golden("next")
+    name = "se_ard_2d_wide"
+    ks = spec(name)
+    pts, y, noise = z[f"next/loglike/{name}/nodes"], z[f"next/loglike/{name}/fvals"], float(z[f"next/loglike/{name}/noise"])
+    noise = 1e-3  # a noise level at which the noise derivative is resolvable by differences
+    g = orc.fast_loglike_gradient(ks, pts, y, noise)
+    h = 1e-6
+    for q in range(2):
+        cl = np.array(ks.cl, dtype=float)
+        up, dn = cl.copy(), cl.copy()
+        up[q] += h
+        dn[q] -= h
+        fd = (orc.fast_loglike(orc.KernelSpec.se(list(up), ks.signal, 2), pts, y, noise) -
+              orc.fast_loglike(orc.KernelSpec.se(list(dn), ks.signal, 2), pts, y, noise)) / (2 * h)
+        assert abs(fd - g["cl%d" % q]) <= 1e-5 * max(1.0, abs(fd))
+    fd = (orc.fast_loglike(orc.KernelSpec.se(list(ks.cl), ks.signal + h, 2), pts, y, noise) -
+          orc.fast_loglike(orc.KernelSpec.se(list(ks.cl), ks.signal - h, 2), pts, y, noise)) / (2 * h)
+    assert abs(fd - g["signalSize"]) <= 1e-5 * max(1.0, abs(fd))
+    # the reference's 'noise' entry is d/d(noise) * 2 * noise (gp.py:463-464)
+    hn = 1e-8
+    fd = (orc.fast_loglike(ks, pts, y, noise + hn) - orc.fast_loglike(ks, pts, y, noise - hn)) / (2 * hn)
+    assert abs(fd * noise * 2.0 - g["noise"]) <= 1e-4 * max(1.0, abs(g["noise"]))
