@@ -214,7 +214,7 @@ def parity_block(ed, gpmod, kernels, Space, ShardedMIEngine, Device, shard, dist
         vpool = np.random.default_rng(43).standard_normal((V, 3))
         eng = ShardedMIEngine(dev, vpool, n, 1e-2, shard=shard)
         mi[tag] = ([int(i) for i in eng.run(n, start=0)], int(eng.info.item()), vpool, n,
-                   int(sum(1 for r in range(world) if eng.bounds[r + 1] == eng.bounds[r])))
+                   int(sum(1 for c in eng.ncols_per_rank if c == 0)))
     torch.cuda.synchronize()
     flat = picks[False] + picks[True] + vidx + mi["mi_1500"][0] + mi["mi_100_empty_ranks"][0]
     t = torch.tensor(flat, device="cuda")

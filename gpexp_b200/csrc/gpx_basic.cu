@@ -458,7 +458,8 @@ extern "C" int gpx_append_row(gpx_handle h, int row_source, const double* rec, c
 __global__ void __launch_bounds__(256) gather_pivot_kernel(const double* __restrict__ W, int64_t ldw, int n,
                                                             const double* __restrict__ var, const double* __restrict__ X,
                                                             int64_t ldx, int d, const double* __restrict__ score,
-                                                            const int64_t* __restrict__ idx, int64_t offset, double noise,
+                                                            const int64_t* __restrict__ idx, int64_t offset,
+                                                            const int64_t* __restrict__ index_map, double noise,
                                                             double* __restrict__ rec) {
     const int64_t p = idx[0];
     if (p < 0) {
@@ -472,7 +473,7 @@ __global__ void __launch_bounds__(256) gather_pivot_kernel(const double* __restr
     if (blockIdx.x == 0) {
         if (threadIdx.x == 0) {
             rec[0] = score ? score[0] : 0.0;
-            rec[1] = (double)(p + offset);
+            rec[1] = (double)(index_map ? index_map[p] : p + offset);
             rec[2] = var[p] + noise;
         }
         if (threadIdx.x < GPX_MAX_DIM) rec[3 + threadIdx.x] = threadIdx.x < d ? X[threadIdx.x * ldx + p] : 0.0;
@@ -482,14 +483,14 @@ __global__ void __launch_bounds__(256) gather_pivot_kernel(const double* __restr
 
 extern "C" int gpx_gather_pivot(gpx_handle h, const double* W, int64_t ldw, int64_t n, const double* var, const double* X,
                                 int64_t ldx, const double* score_dev, const int64_t* idx_dev, int64_t index_offset,
-                                double noise, double* rec, void* stream) {
+                                const int64_t* index_map, double noise, double* rec, void* stream) {
     GPX_NEED_KERNEL(h);
     GPX_REQUIRE(n >= 0 && var && X && idx_dev && rec && (W || n == 0), GPX_EINVAL, "bad arguments");
     unsigned grid = (unsigned)((n + 255) / 256);
     if (grid < 1) grid = 1;
     if (grid > 64) grid = 64;
     gather_pivot_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, ldw, (int)n, var, X, ldx, h->kp.d, score_dev, idx_dev,
-                                                              index_offset, noise, rec);
+                                                              index_offset, index_map, noise, rec);
     return gpx_check_launch("gpx_gather_pivot");
 }
 
@@ -663,8 +664,15 @@ extern "C" int gpx_score_mi(gpx_handle h, const double* num_var, const double* p
 // are added in row-chunk order by a second kernel (deterministic).  Blocks above the diagonal write zeros.
 #define MI_KCH 256
 
+// global column of local column i: contiguous slice (blk = 0: i + col_offset) or block-cyclic (local block i / blk of rank
+// `col_offset` among `world` ranks is global block (i / blk) * world + col_offset)
+__device__ __forceinline__ int64_t mi_global_col(int64_t i, int64_t col_offset, int64_t blk, int64_t world) {
+    return blk > 0 ? ((i / blk) * world + col_offset) * blk + (i % blk) : i + col_offset;
+}
+
 __global__ void __launch_bounds__(128) mi_prec_partial_kernel(const double* __restrict__ Y, int64_t nrows, int64_t ncols,
-                                                               int64_t ldy, int64_t col_offset, const int64_t* __restrict__ pdev,
+                                                               int64_t ldy, int64_t col_offset, int64_t blk, int64_t world,
+                                                               const int64_t* __restrict__ pdev,
                                                                const double* __restrict__ ycol, double* __restrict__ part) {
     __shared__ double syp[MI_KCH];
     const int64_t p = pdev[0];  // GLOBAL index of the pivot column
@@ -673,7 +681,8 @@ __global__ void __launch_bounds__(128) mi_prec_partial_kernel(const double* __re
     int64_t k1 = k0 + MI_KCH;
     if (k1 > nrows) k1 = nrows;
     double* dst = part + (int64_t)blockIdx.y * ldy;
-    const int64_t i0g = (int64_t)blockIdx.x * 256 + col_offset;  // smallest global column of the block
+    // smallest global column of the block (256 local columns never straddle a cyclic block: blk is a multiple of 256 or 0)
+    const int64_t i0g = mi_global_col((int64_t)blockIdx.x * 256, col_offset, blk, world);
     const int64_t lo_blk = i0g > p ? i0g : p;
     if (p < 0 || k1 <= lo_blk) {  // nothing in this row chunk reaches these columns
         if (i < ncols) {
@@ -684,10 +693,10 @@ __global__ void __launch_bounds__(128) mi_prec_partial_kernel(const double* __re
     }
     // column p of Y: from the dense vector when given (sharded pools), else from the local matrix
     for (int t = threadIdx.x; t < MI_KCH; t += 128)
-        syp[t] = (k0 + t < k1) ? (ycol ? ycol[k0 + t] : Y[(k0 + t) * ldy + (p - col_offset)]) : 0.0;
+        syp[t] = (k0 + t < k1) ? (ycol ? ycol[k0 + t] : Y[(k0 + t) * ldy + (p - col_offset)]) : 0.0;  // ycol == NULL: dense, blk == 0
     __syncthreads();
     if (i >= ncols) return;
-    const int64_t ig = i + col_offset;
+    const int64_t ig = mi_global_col(i, col_offset, blk, world);
     int64_t k = ig > p ? ig : p;  // column i+1 also starts here: Y[i, i+1] = 0 is stored explicitly
     if (k < k0) k = k0;
     double a0 = 0.0, a1 = 0.0;
@@ -727,9 +736,11 @@ extern "C" int64_t gpx_mi_prec_column_workspace(int64_t nrows, int64_t ldy) {
 }
 
 extern "C" int gpx_mi_prec_column(gpx_handle h, const double* Y, int64_t nrows, int64_t ncols, int64_t ldy,
-                                  int64_t col_offset, const int64_t* p_dev, const double* ycol, double* workspace,
-                                  double* out, void* stream) {
+                                  int64_t col_offset, int64_t cyclic_blk, int64_t cyclic_world, const int64_t* p_dev,
+                                  const double* ycol, double* workspace, double* out, void* stream) {
     GPX_REQUIRE(h && Y && p_dev && out && workspace && nrows >= 1 && ncols >= 1 && col_offset >= 0, GPX_EINVAL, "bad arguments");
+    GPX_REQUIRE(cyclic_blk == 0 || (cyclic_blk % 256 == 0 && cyclic_world >= 1 && col_offset < cyclic_world && ycol != nullptr),
+                GPX_EINVAL, "block-cyclic slices: blk a multiple of 256, col_offset = rank < world, pivot column as a vector");
     GPX_REQUIRE((ldy % 2) == 0 && ldy >= ncols + (ncols & 1) && gpx_aligned16(Y), GPX_EALIGN,
                 "Y must be 16-byte aligned with an even leading dimension");
     GPX_REQUIRE(ycol != nullptr || (col_offset == 0 && ncols == nrows), GPX_EINVAL,
@@ -738,7 +749,8 @@ extern "C" int gpx_mi_prec_column(gpx_handle h, const double* Y, int64_t nrows, 
     GPX_REQUIRE(nchunks <= 65535, GPX_ESIZE, "pool too large for one launch");
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid((unsigned)((ncols + 255) / 256), (unsigned)nchunks);
-    mi_prec_partial_kernel<<<grid, 128, 0, st>>>(Y, nrows, ncols, ldy, col_offset, p_dev, ycol, workspace);
+    mi_prec_partial_kernel<<<grid, 128, 0, st>>>(Y, nrows, ncols, ldy, col_offset, cyclic_blk, cyclic_world, p_dev, ycol,
+                                                 workspace);
     int rc = gpx_check_launch("gpx_mi_prec_column partial");
     if (rc) return rc;
     mi_prec_reduce_kernel<<<(unsigned)((ncols + 255) / 256), 256, 0, st>>>(workspace, (int)nchunks, ncols, ldy, out);
@@ -778,6 +790,41 @@ extern "C" int gpx_local_index(gpx_handle h, const double* rec, int64_t offset, 
     GPX_REQUIRE(h && rec && out2, GPX_EINVAL, "bad arguments");
     local_index_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(rec, offset, count, out2);
     return gpx_check_launch("gpx_local_index");
+}
+
+// block-cyclic ownership: global index g lives on rank (g / blk) % world at local index ((g / blk) / world) * blk + g % blk
+__global__ void local_index_cyclic_kernel(const double* __restrict__ rec, int64_t blk, int64_t world, int64_t rank, int64_t count,
+                                          int64_t* out) {
+    const int64_t g = (int64_t)rec[1];
+    int64_t loc = -1;
+    if (rec[1] >= 0.0 && (g / blk) % world == rank) {
+        loc = ((g / blk) / world) * blk + g % blk;
+        if (loc >= count) loc = -1;
+    }
+    out[0] = loc;
+    out[1] = g;
+}
+
+extern "C" int gpx_local_index_cyclic(gpx_handle h, const double* rec, int64_t blk, int64_t world, int64_t rank, int64_t count,
+                                      int64_t* out2, void* stream) {
+    GPX_REQUIRE(h && rec && out2 && blk >= 1 && world >= 1 && rank >= 0 && rank < world, GPX_EINVAL, "bad arguments");
+    local_index_cyclic_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(rec, blk, world, rank, count, out2);
+    return gpx_check_launch("gpx_local_index_cyclic");
+}
+
+// A[rows[j] * ld + j] += value for j < n : the diagonal of a matrix whose columns are a scattered subset of a square one
+__global__ void __launch_bounds__(256) add_at_rows_kernel(double* __restrict__ A, int64_t ld, const int64_t* __restrict__ rows,
+                                                           int64_t n, double value) {
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j < n) A[rows[j] * ld + j] += value;
+}
+
+extern "C" int gpx_add_at_rows(gpx_handle h, double* A, int64_t ld, const int64_t* rows, int64_t n, double value, void* stream) {
+    GPX_REQUIRE(h && n >= 0, GPX_EINVAL, "bad arguments");
+    if (n == 0) return GPX_OK;
+    GPX_REQUIRE(A && rows && ld >= n, GPX_EINVAL, "bad arguments");
+    add_at_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(A, ld, rows, n, value);
+    return gpx_check_launch("gpx_add_at_rows");
 }
 
 

@@ -88,6 +88,10 @@ struct CoreArgs {
     int tiles_per_cta; // IVAR: i-tiles each CTA walks
     int upper_only;    // SUB: skip tiles below the diagonal ; ivar_ws_kernel: candidate tiles per wave group
     int ldo_splits;    // ivar_ws_kernel: number of M-splits
+    // sub_ws_kernel: operand B is this rank's column slice of a LOWER-triangular matrix distributed block-cyclically
+    // (local column j = block j / tri_blk of this rank = global block (j / tri_blk) * tri_world + tri_rank): rows above the
+    // first global column of a tile are structurally zero and are skipped.  tri_blk = 0: dense operand.
+    int tri_blk, tri_world, tri_rank;
 };
 
 __device__ __forceinline__ void cp_async16(double* dst, const double* src, bool ok) {
@@ -761,9 +765,10 @@ __global__ void __launch_bounds__(256, 1) ivar_ws_kernel(const __grid_constant__
 constexpr int SUBWS_SMEM_DOUBLES = WS_STAGES * WS_STAGE + 2 * WS_STAGES;
 constexpr size_t SUBWS_SMEM_BYTES = (size_t)SUBWS_SMEM_DOUBLES * sizeof(double);
 
-__global__ void __launch_bounds__(256, 1) sub_ws_kernel(const __grid_constant__ CoreArgs a) {
+template <bool TMAP>
+__global__ void __launch_bounds__(256, 1) sub_ws_kernel(const __grid_constant__ CoreArgs a, const __grid_constant__ TmaMaps maps) {
     constexpr int BM = WS_BM, LD = WS_LD, NW = 8;
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(128) double smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + WS_STAGES * WS_STAGE);
     uint64_t* empty = full + WS_STAGES;
 
@@ -772,7 +777,15 @@ __global__ void __launch_bounds__(256, 1) sub_ws_kernel(const __grid_constant__ 
     const int64_t j0 = (int64_t)blockIdx.x * BN;
     const int64_t i0 = (int64_t)blockIdx.y * BM;
     if (a.upper_only && i0 >= j0 + BN) return;  // tile strictly below the diagonal of a symmetric update
-    const int G = (a.K + WS_BK - 1) / WS_BK;     // chunks
+    // first K chunk that can hold a non-zero of this column tile (lower-triangular B: rows < global column are zero)
+    int c_begin = 0;
+    if (a.tri_blk > 0) {
+        const int64_t gcol = ((j0 / a.tri_blk) * a.tri_world + a.tri_rank) * a.tri_blk + (j0 % a.tri_blk);
+        c_begin = (int)(gcol / WS_BK);
+    }
+    const int c_end = (a.K + WS_BK - 1) / WS_BK;
+    const int G = c_end > c_begin ? c_end - c_begin : 0;  // chunks this CTA walks: c_begin + g
+    if (G == 0) return;
 
     if (tid == 0) {
 #pragma unroll
@@ -787,18 +800,28 @@ __global__ void __launch_bounds__(256, 1) sub_ws_kernel(const __grid_constant__ 
     const int wm = warp & 3, wn = warp >> 2;
     const int g4 = lane >> 2, q4 = lane & 3;
 
-    auto produce = [&](int c) {
-        if (c >= G) return;
-        const int s = c % WS_STAGES;
-        const unsigned int ph = (unsigned int)(c / WS_STAGES) & 1u;
+    auto produce = [&](int g) {
+        if (g >= G) return;
+        const int c = c_begin + g;
+        const int s = g % WS_STAGES;
+        const unsigned int ph = (unsigned int)(g / WS_STAGES) & 1u;
         mbar_wait(empty + s, ph ^ 1u);
+        double* stA = smem + s * WS_STAGE;
+        double* stB = stA + WS_BK * LD;
+        if (TMAP) {
+            if (lane == 0) {
+                mbar_arrive_expect_tx(full + s, (unsigned int)WS_BK * 2u * LD * 8u);
+                tma_load_2d(stA, &maps.a_main, (int)i0, c * WS_BK, full + s);
+                tma_load_2d(stB, &maps.b_main, (int)j0, c * WS_BK, full + s);
+            }
+            __syncwarp();
+            return;
+        }
         const double* srcA = a.A + (int64_t)c * WS_BK * a.lda + i0;
         const double* srcB = a.B + (int64_t)c * WS_BK * a.ldb + j0;
         const int rem = a.K - c * WS_BK;
         const int krows = rem < WS_BK ? rem : WS_BK;
         const int ksteps = rem >= WS_BK ? WS_KSTEPS : ((rem + 3) >> 2);
-        double* stA = smem + s * WS_STAGE;
-        double* stB = stA + WS_BK * LD;
         if (krows < ksteps * 4) {
             for (int r = krows; r < ksteps * 4; ++r) {
                 for (int cc = lane * 2; cc < BM; cc += 64) {
@@ -836,12 +859,20 @@ __global__ void __launch_bounds__(256, 1) sub_ws_kernel(const __grid_constant__ 
         mbar_wait(full + s, ph);
         const double* pa = smem + s * WS_STAGE + fa;
         const double* pb = smem + s * WS_STAGE + fb;
-        const int rem = a.K - g * WS_BK;
-        const int ksteps = rem >= WS_BK ? WS_KSTEPS : ((rem + 3) >> 2);
+        const int rem = a.K - (c_begin + g) * WS_BK;
+        if (rem >= WS_BK) {
+#pragma unroll
+            for (int ks = 0; ks < WS_KSTEPS; ++ks) {
+                load_frags_ws(af0, bf0, pa, pb, ks);
+                mma_tile(acc, af0, bf0);
+            }
+        } else {
+            const int ksteps = (rem + 3) >> 2;
 #pragma unroll 1
-        for (int ks = 0; ks < ksteps; ++ks) {
-            load_frags_ws(af0, bf0, pa, pb, ks);
-            mma_tile(acc, af0, bf0);
+            for (int ks = 0; ks < ksteps; ++ks) {
+                load_frags_ws(af0, bf0, pa, pb, ks);
+                mma_tile(acc, af0, bf0);
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
@@ -1024,6 +1055,7 @@ int gpx_launch_core_ivar(gpx_handle h, int prologue, const double* Wm, int64_t l
     a.tiles_per_cta = (int)((itl + splits - 1) / splits);
     a.upper_only = 0;
     a.ldo_splits = 0;
+    a.tri_blk = a.tri_world = a.tri_rank = 0;
     *nsplit_out = splits;
     if (tma) {
         const int64_t jt = (C + BN - 1) / BN;
@@ -1078,6 +1110,7 @@ int gpx_launch_core_store(gpx_handle h, int prologue, const double* A, int64_t l
     a.tiles_per_cta = 1;
     a.upper_only = 0;
     a.ldo_splits = 0;
+    a.tri_blk = a.tri_world = a.tri_rank = 0;
     const int64_t jt = (J + BN - 1) / BN, it = (I + Cfg::BM - 1) / Cfg::BM;
     if (prologue == PRO_DIFF) {
         GPX_DISPATCH_FAMILY(h->kp.family, rc = (launch_core<FAM, EPI_STORE, PRO_DIFF>(h, a, jt, it, st)));
@@ -1113,13 +1146,17 @@ extern "C" int gpx_dgemm_tn_sub(gpx_handle h, const double* A, int64_t lda, cons
     a.tiles_per_cta = 1;
     a.upper_only = upper_only;
     a.ldo_splits = 0;
+    a.tri_blk = a.tri_world = a.tri_rank = 0;
     return launch_core<GPX_SE, EPI_SUB, PRO_NONE>(h, a, (J + BN - 1) / BN, (I + Cfg::BM - 1) / Cfg::BM, (cudaStream_t)stream);
 }
 
 // Same update for operands the CALLER guarantees to be fully padded (every 128-wide tile of A's I columns and B's J
-// columns readable and finite, lda/ldb multiples of 128 or at least covering the rounded-up extents): TMA + mbarrier kernel.
-extern "C" int gpx_dgemm_tn_sub_padded(gpx_handle h, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
-                                       int64_t ldc, int64_t I, int64_t J, int64_t K, int upper_only, void* stream) {
+// columns readable and finite, lda/ldb multiples of 128 or at least covering the rounded-up extents): TMA + mbarrier kernel,
+// one 2-D tensor-map load per operand chunk.  tri_blk > 0 declares B the local column slice of a lower-triangular matrix
+// in a block-cyclic distribution (see CoreArgs): its structurally-zero leading rows are skipped per column tile.
+static int dgemm_tn_sub_ws(gpx_handle h, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                           int64_t I, int64_t J, int64_t K, int upper_only, int tri_blk, int tri_world, int tri_rank,
+                           void* stream) {
     GPX_REQUIRE(h != nullptr, GPX_EINVAL, "handle is NULL");
     GPX_REQUIRE(I >= 0 && J >= 0 && K >= 0, GPX_EINVAL, "negative size");
     if (I == 0 || J == 0 || K == 0) return GPX_OK;
@@ -1131,6 +1168,8 @@ extern "C" int gpx_dgemm_tn_sub_padded(gpx_handle h, const double* A, int64_t ld
     if ((rc = check_operand(C, ldc, "C"))) return rc;
     GPX_REQUIRE(lda >= (I + WS_BM - 1) / WS_BM * WS_BM && ldb >= (J + BN - 1) / BN * BN, GPX_EALIGN,
                 "padded variant needs leading dimensions that cover whole 128-wide tiles");
+    GPX_REQUIRE(tri_blk == 0 || (tri_blk % BN == 0 && tri_world >= 1 && tri_rank >= 0 && tri_rank < tri_world), GPX_EINVAL,
+                "block-cyclic description: blk must be a multiple of 128, 0 <= rank < world");
     CoreArgs a;
     a.A = A;
     a.B = B;
@@ -1146,10 +1185,31 @@ extern "C" int gpx_dgemm_tn_sub_padded(gpx_handle h, const double* A, int64_t ld
     a.tiles_per_cta = 1;
     a.upper_only = upper_only;
     a.ldo_splits = 0;
-    if ((rc = gpx_ensure_smem(h, (const void*)sub_ws_kernel, SUBWS_SMEM_BYTES, "sub_ws"))) return rc;
+    a.tri_blk = tri_blk;
+    a.tri_world = tri_world;
+    a.tri_rank = tri_rank;
     dim3 grid((unsigned)((J + BN - 1) / BN), (unsigned)((I + WS_BM - 1) / WS_BM));
-    sub_ws_kernel<<<grid, 256, SUBWS_SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    TmaMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    if (encode_tiled() && make_map(&maps.a_main, A, lda, K, WS_BK) == GPX_OK && make_map(&maps.b_main, B, ldb, K, WS_BK) == GPX_OK) {
+        if ((rc = gpx_ensure_smem(h, (const void*)sub_ws_kernel<true>, SUBWS_SMEM_BYTES, "sub_ws"))) return rc;
+        sub_ws_kernel<true><<<grid, 256, SUBWS_SMEM_BYTES, (cudaStream_t)stream>>>(a, maps);
+    } else {
+        if ((rc = gpx_ensure_smem(h, (const void*)sub_ws_kernel<false>, SUBWS_SMEM_BYTES, "sub_ws"))) return rc;
+        sub_ws_kernel<false><<<grid, 256, SUBWS_SMEM_BYTES, (cudaStream_t)stream>>>(a, maps);
+    }
     return gpx_check_launch("gpx_dgemm_tn_sub_padded");
+}
+
+extern "C" int gpx_dgemm_tn_sub_padded(gpx_handle h, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                                       int64_t ldc, int64_t I, int64_t J, int64_t K, int upper_only, void* stream) {
+    return dgemm_tn_sub_ws(h, A, lda, B, ldb, C, ldc, I, J, K, upper_only, 0, 0, 0, stream);
+}
+
+extern "C" int gpx_dgemm_tn_sub_lower(gpx_handle h, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                                      int64_t ldc, int64_t I, int64_t J, int64_t K, int blk, int world, int rank, void* stream) {
+    GPX_REQUIRE(blk > 0, GPX_EINVAL, "blk must be positive");
+    return dgemm_tn_sub_ws(h, A, lda, B, ldb, C, ldc, I, J, K, 0, blk, world, rank, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -113,17 +113,20 @@ class _Pivoting:
     def _gather(self, W, ld, var, X: PointSet, noise: float, minimize: bool):
         dev = self.dev
         check(lib.gpx_gather_pivot(dev.h, ptr(W), ld, self.n, ptr(var), ptr(X.X), X.ld, ptr(self.best), ptr(self.idx),
-                                   self.index_offset, noise, ptr(self.rec), dev.stream), "gpx_gather_pivot")
+                                   self.index_offset, ptr(getattr(self, "index_map", None)), noise, ptr(self.rec), dev.stream),
+              "gpx_gather_pivot")
         if self.rec_all is not None:
             self.shard.all_gather(self.rec_all, self.rec)
             check(lib.gpx_select_pivot(dev.h, ptr(self.rec_all), self.shard.world, self.reclen, self.n,
                                        1 if minimize else 0, ptr(self.rec_win), dev.stream), "gpx_select_pivot")
 
+    def _local_of(self, global_index: int) -> int:
+        local = global_index - self.index_offset
+        return local if 0 <= local < self._local_count() else -1
+
     def _force_local(self, global_index: int):
         """Make `global_index` the pivot of this step (seeds / given designs): owner rank points at it."""
-        local = global_index - self.index_offset
-        if not (0 <= local < self._local_count()):
-            local = -1
+        local = self._local_of(global_index)
         self.idx.fill_(local)
         self.best.zero_()
 
@@ -724,10 +727,10 @@ class GreedyMIEngine(_Pivoting):
         self._gather(self.W, ld, self.num, pool, self.noise, minimize=False)
         check(lib.gpx_append_row(dev.h, _lib.ROW_KERNEL, ptr(self.rec), None, ptr(pool.X), v, ld, ptr(self.W), ld, self.n,
                                  ptr(self.num), dev.stream), "gpx_append_row")
-        check(lib.gpx_mi_prec_column(dev.h, ptr(self.Y), v, v, ld, 0, ptr(self.idx), None, ptr(self.pws), ptr(self.pcol),
+        check(lib.gpx_mi_prec_column(dev.h, ptr(self.Y), v, v, ld, 0, 0, 1, ptr(self.idx), None, ptr(self.pws), ptr(self.pcol),
                                      dev.stream), "gpx_mi_prec_column")
-        check(lib.gpx_gather_pivot(dev.h, ptr(self.Us), ld, self.n, ptr(self.pd), ptr(pool.X), ld, None, ptr(self.idx), 0, 0.0,
-                                   ptr(self.rec2), dev.stream), "gpx_gather_pivot")
+        check(lib.gpx_gather_pivot(dev.h, ptr(self.Us), ld, self.n, ptr(self.pd), ptr(pool.X), ld, None, ptr(self.idx), 0, None,
+                                   0.0, ptr(self.rec2), dev.stream), "gpx_gather_pivot")
         check(lib.gpx_append_row(dev.h, _lib.ROW_MATRIX, ptr(self.rec2), ptr(self.pcol), None, v, ld, ptr(self.Us), ld, self.n,
                                  ptr(self.pd), dev.stream), "gpx_append_row")
         check(lib.gpx_set_mask(dev.h, ptr(self.mask), ptr(self.idx), 1, dev.stream), "gpx_set_mask")
@@ -761,91 +764,104 @@ class ShardedMIEngine(_Pivoting):
     """Greedy mutual information with the |V| x |V| matrices sharded by COLUMN BLOCKS over the ranks
     (cfg-4 at full size: 200 000^2 doubles do not fit one GPU).
 
-    Set-up, left-looking in 128-row blocks, every rank holding its columns [lo, hi) of both matrices:
-        panel  P = U[0:kb, kb:kb+128]            broadcast from the owner of column block kb
-        U[kb blk, my cols >= kb]   = U_kk^-T (A[kb blk, .] - P^T U[0:kb, .])     DMMA update + forward substitution
-        Y[kb blk, my cols < kb+128] = U_kk^-T (I[kb blk, .] - P^T Y[0:kb, .])    (Y = U^-T, lower triangular)
-    so that K_VV + noise I = U^T U and (K_VV + noise I)^-1 = Y^T Y without any rank ever holding a full matrix.
-    Both updates reuse the same broadcast panel and together touch every local column once per block: balanced.
+    Distribution: block-cyclic -- global column block g (BLK columns) lives on rank g % world as its local block g // world,
+    so every rank owns the same share of every part of both triangles and each elimination step is balanced.
+
+    Set-up, left-looking in BLK-row blocks, every rank holding its columns of both matrices:
+        panel  P = U[0:kb, kb:kb+BLK]                 broadcast from the owner of column block kb / BLK
+        U[kb blk, my cols >= kb]    = U_kk^-T (A[kb blk, .] - P^T U[0:kb, .])     DMMA update + forward substitution
+        Y[kb blk, my cols < kb+BLK] = U_kk^-T (I[kb blk, .] - P^T Y[0:kb, .])     (Y = U^-T, lower triangular: the rows of a
+                                                                                   column tile above its own global column
+                                                                                   are zero and skipped inside the kernel)
+    so that K_VV + noise I = U^T U and (K_VV + noise I)^-1 = Y^T Y without any rank ever holding a full matrix.  Executed
+    work: V^3/3 (U) + V^3/3 (Y) flop, the useful amount.
     Per greedy step: one all_gather of numerator pivot records, one all_reduce that carries column p of Y (and of the
     downdate vectors) from its owner to everybody, then purely local kernels.
     """
 
-    BLK = 512  # rows per elimination block (GPX_MI_BLK overrides; multiples of 128). 2 GPUs, |V| = 40 000: 128 -> 2.06 s, 256 -> 1.64 s, 512 -> 1.45 s
+    BLK = 512  # columns per distribution block = rows per elimination block (GPX_MI_BLK overrides; power of two >= 256)
 
     def __init__(self, dev: Device, pool_host: np.ndarray, n_max: int, noise: float, shard=None):
         import os
         self.BLK = int(os.environ.get("GPX_MI_BLK", self.BLK))
-        if self.BLK < 128 or self.BLK & (self.BLK - 1):
-            # column offsets handed to gpx_dgemm_tn_sub_padded must stay multiples of the 128-wide TMA tiles while the
-            # block size is halved for small pools
-            raise ValueError(f"GPX_MI_BLK must be a power of two >= 128, got {self.BLK}")
+        if self.BLK < 256 or self.BLK & (self.BLK - 1):
+            # tiles of the TMA update kernel (128 columns) and of the precision-column kernel (256) must not straddle blocks
+            raise ValueError(f"GPX_MI_BLK must be a power of two >= 256, got {self.BLK}")
         import torch.distributed as dist
         self.dist = dist
         self.noise = float(noise)
         world = shard.world if shard is not None else 1
         rank = shard.rank if shard is not None else 0
+        self.world, self.rank = world, rank
         V = pool_host.shape[0]
         self.V = V
-        # keep at least ~4 elimination blocks per rank so that the column ranges stay balanced on small pools
-        while self.BLK > 128 and (V + self.BLK - 1) // self.BLK < 4 * world:
+        # keep a few elimination blocks per rank on small pools
+        while self.BLK > 256 and (V + self.BLK - 1) // self.BLK < 4 * world:
             self.BLK //= 2
-        nblk = (V + self.BLK - 1) // self.BLK
-        self.bounds = [min(Shard.split(nblk, world, r)[0] * self.BLK, V) for r in range(world)] + [V]
-        lo, hi = self.bounds[rank], self.bounds[rank + 1]
-        self.lo, self.hi = lo, hi
-        nloc = hi - lo
+        B = self.BLK
+        nblk = (V + B - 1) // B
+        gcols = self.cyclic_columns(V, B, world, rank)
+        self.gcols = gcols                                           # global column of every local column
+        nloc = int(gcols.size)
+        self.nloc = nloc
+        self.ncols_per_rank = [sum(min((g + 1) * B, V) - g * B for g in range(r, nblk, world)) for r in range(world)]
         ncap = max(int(n_max), 1)
-        self._init_pivot(dev, ncap, n_max, shard, lo)
-        self.pool = dev.points(pool_host[lo:hi])
+        self._init_pivot(dev, ncap, n_max, shard, 0)
+        self.pool = dev.points(pool_host[gcols]) if nloc else dev.points(pool_host[:0])
         allpts = dev.points(pool_host)
         ld = self.pool.ld
         self.ld = ld
+        self.index_map = dev.upload(self.gcols, dtype=torch.int64) if nloc else dev.zeros(1, dtype=torch.int64)
         st = dev.stream
-        # ---- local slices of K_VV + noise I (rows 0..hi are enough: only the upper triangle is read) and of I
+        # ---- local columns of K_VV + noise I and of the identity (all V rows: only rows <= column are read)
         A = dev.zeros(V, ld)
-        if lo > 0:
-            check(lib.gpx_gram(dev.h, ptr(allpts.X), lo, allpts.ld, ptr(self.pool.X), nloc, ld, ptr(A), ld, 0, None, 0.0, st), "gpx_gram")
-        if nloc > 0:
-            check(lib.gpx_gram(dev.h, ptr(self.pool.X), nloc, ld, ptr(self.pool.X), nloc, ld, ptr(A[lo:]), ld, 1, None,
-                               self.noise, st), "gpx_gram")
         Y = dev.zeros(V, ld)
         if nloc > 0:
-            Y[lo:hi, :nloc].fill_diagonal_(1.0)
-        panel = dev.zeros(V, self.BLK)
-        diag = dev.zeros(self.BLK, self.BLK)  # the factored diagonal block travels as a dense BLK x BLK matrix
+            check(lib.gpx_gram(dev.h, ptr(allpts.X), V, allpts.ld, ptr(self.pool.X), nloc, ld, ptr(A), ld, 0, None, 0.0, st), "gpx_gram")
+            check(lib.gpx_add_at_rows(dev.h, ptr(A), ld, ptr(self.index_map), nloc, self.noise, st), "gpx_add_at_rows")
+            check(lib.gpx_add_at_rows(dev.h, ptr(Y), ld, ptr(self.index_map), nloc, 1.0, st), "gpx_add_at_rows")
+        del allpts
+        panel = dev.zeros(V, B)
+        diag = dev.zeros(B, B)  # the factored diagonal block travels as a dense BLK x BLK matrix
         info = dev.zeros(1, dtype=torch.int32)
         bad = dev.zeros(1, dtype=torch.int32)
         group = shard.group if shard is not None else None
-        B = self.BLK
-        for kb in range(0, V, B):
+
+        def first_local_block_at_or_after(g):  # smallest local block j with global block rank + j*world >= g
+            return max(0, -(-(g - rank) // world))
+
+        for g in range(nblk):
+            kb = g * B
             b = min(B, V - kb)
-            owner = max(r for r in range(world) if self.bounds[r] <= kb)
-            mine = rank == owner
+            owner = g % world
+            own = rank == owner
+            jl = g // world                     # local block index on the owner
             if kb > 0:
-                if mine:
-                    panel[:kb, :b].copy_(A[:kb, kb - lo: kb - lo + b])
+                if own:
+                    panel[:kb, :b].copy_(A[:kb, jl * B: jl * B + b])
                 if world > 1:
                     dist.broadcast(panel[:kb], src=owner, group=group)
-                cu = max(lo, kb) - lo
+                # U: my columns in global blocks >= g (a suffix of the local columns)
+                cu = min(first_local_block_at_or_after(g) * B, nloc)
                 if nloc - cu > 0:
                     # panel, A and Y are allocated in whole 128-wide tiles: the TMA update kernel may read full tiles
                     check(lib.gpx_dgemm_tn_sub_padded(dev.h, ptr(panel), B, ptr(A) + 8 * cu, ld, ptr(A) + 8 * (kb * ld + cu), ld,
                                                       b, nloc - cu, kb, 0, st), "gpx_dgemm_tn_sub_padded")
-                ny = min(hi, kb + b) - lo
+                # Y: my columns in global blocks <= g (a prefix); rows above each tile's own column are skipped in-kernel
+                ny = min(first_local_block_at_or_after(g + 1) * B, nloc)
                 if ny > 0:
-                    check(lib.gpx_dgemm_tn_sub_padded(dev.h, ptr(panel), B, ptr(Y), ld, ptr(Y) + 8 * kb * ld, ld, b, ny, kb, 0,
-                                                      st), "gpx_dgemm_tn_sub_padded")
-            if mine:
-                check(lib.gpx_potrf(dev.h, ptr(A) + 8 * (kb * ld + kb - lo), b, ld, ptr(info), st), "gpx_potrf")
+                    check(lib.gpx_dgemm_tn_sub_lower(dev.h, ptr(panel), B, ptr(Y), ld, ptr(Y) + 8 * kb * ld, ld, b, ny, kb, B,
+                                                     world, rank, st), "gpx_dgemm_tn_sub_lower")
+            if own:
+                check(lib.gpx_potrf(dev.h, ptr(A) + 8 * (kb * ld + jl * B), b, ld, ptr(info), st), "gpx_potrf")
                 bad.copy_(torch.maximum(bad, torch.where(info > 0, info + kb, info)))
-                diag[:b, :b].copy_(A[kb: kb + b, kb - lo: kb - lo + b])
+                diag[:b, :b].copy_(A[kb: kb + b, jl * B: jl * B + b])
             if world > 1:
                 dist.broadcast(diag, src=owner, group=group)
-            cs = max(lo, kb + b) - lo
+            cs = min(first_local_block_at_or_after(g + 1) * B, nloc)   # my columns in global blocks > g
             if nloc - cs > 0:
                 check(lib.gpx_trsm(dev.h, ptr(diag), b, B, ptr(A) + 8 * (kb * ld + cs), nloc - cs, ld, st), "gpx_trsm")
-            ny = min(hi, kb + b) - lo
+            ny = cs                                                      # ... and in global blocks <= g
             if ny > 0:
                 check(lib.gpx_trsm(dev.h, ptr(diag), b, B, ptr(Y) + 8 * kb * ld, ny, ld, st), "gpx_trsm")
         if world > 1:
@@ -855,13 +871,26 @@ class ShardedMIEngine(_Pivoting):
         del A, panel
         self._init_greedy(n_max)
 
+    @staticmethod
+    def cyclic_columns(V: int, B: int, world: int, rank: int) -> np.ndarray:
+        """Global columns owned by `rank`, in local order: blocks rank, rank + world, ... of B columns."""
+        blocks = range(rank, (V + B - 1) // B, world)
+        parts = [np.arange(g * B, min((g + 1) * B, V), dtype=np.int64) for g in blocks]
+        return np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+
+    @staticmethod
+    def cyclic_local(g: int, V: int, B: int, world: int, rank: int) -> int:
+        if not (0 <= g < V) or (g // B) % world != rank:
+            return -1
+        return ((g // B) // world) * B + g % B
+
     def _init_greedy(self, n_max: int):
         """(Re)start the greedy state on the factorisation already held: nothing chosen, denominators from diag(Y^T Y)."""
         dev, ld, V = self.dev, self.ld, self.V
-        nloc = self.hi - self.lo
+        nloc = self.nloc
         st = dev.stream
         ncap = max(int(n_max), 1)
-        self._init_pivot(dev, ncap, n_max, self.shard, self.lo)
+        self._init_pivot(dev, ncap, n_max, self.shard, 0)
         self.pd = dev.zeros(ld)
         if nloc > 0:
             check(lib.gpx_colsumsq(dev.h, ptr(self.Y), V, nloc, ld, None, ptr(self.pd), st), "gpx_colsumsq")
@@ -884,11 +913,20 @@ class ShardedMIEngine(_Pivoting):
         self._init_greedy(n_max)
 
     def _local_count(self):
-        return self.hi - self.lo
+        return self.nloc
+
+    def _local_of(self, global_index: int) -> int:
+        return self.cyclic_local(int(global_index), self.V, self.BLK, self.world, self.rank)
+
+    def global_scores(self) -> np.ndarray:
+        """This rank's scores scattered to global candidate positions (NaN where another rank owns the candidate)."""
+        out = np.full(self.V, np.nan)
+        out[self.gcols] = self.scores[: self.nloc].cpu().numpy()
+        return out
 
     def score(self):
         dev = self.dev
-        nloc = self.hi - self.lo
+        nloc = self.nloc
         if nloc == 0:  # a rank without columns (more ranks than blocks) only takes part in the exchanges
             self.idx.fill_(-1)
             self.best.zero_()
@@ -898,12 +936,13 @@ class ShardedMIEngine(_Pivoting):
 
     def take(self):
         dev, pool, ld, V = self.dev, self.pool, self.ld, self.V
-        nloc = self.hi - self.lo
+        nloc = self.nloc
         st = dev.stream
         self._gather(self.W, ld, self.num, pool, self.noise, minimize=False)
         check(lib.gpx_append_row(dev.h, _lib.ROW_KERNEL, ptr(self.rec_win), None, ptr(pool.X), nloc, ld, ptr(self.W), ld,
                                  self.n, ptr(self.num), st), "gpx_append_row")
-        check(lib.gpx_local_index(dev.h, ptr(self.rec_win), self.lo, nloc, ptr(self.loc2), st), "gpx_local_index")
+        check(lib.gpx_local_index_cyclic(dev.h, ptr(self.rec_win), self.BLK, self.world, self.rank, nloc, ptr(self.loc2), st),
+              "gpx_local_index_cyclic")
         self.buf.zero_()
         bufY, bufU = self.buf[: self.bufY_len], self.buf[self.bufY_len:]
         if nloc > 0:
@@ -914,8 +953,8 @@ class ShardedMIEngine(_Pivoting):
         if self.rec_all is not None:
             self.dist.all_reduce(self.buf, op=self.dist.ReduceOp.SUM, group=self.shard.group)
         if nloc > 0:
-            check(lib.gpx_mi_prec_column(dev.h, ptr(self.Y), V, nloc, ld, self.lo, ptr(self.loc2) + 8, ptr(bufY) + 8 * HDR,
-                                         ptr(self.pws), ptr(self.pcol), st), "gpx_mi_prec_column")
+            check(lib.gpx_mi_prec_column(dev.h, ptr(self.Y), V, nloc, ld, self.rank, self.BLK, self.world, ptr(self.loc2) + 8,
+                                         ptr(bufY) + 8 * HDR, ptr(self.pws), ptr(self.pcol), st), "gpx_mi_prec_column")
             check(lib.gpx_append_row(dev.h, _lib.ROW_MATRIX, ptr(bufU), ptr(self.pcol), None, nloc, ld, ptr(self.Us), ld,
                                      self.n, ptr(self.pd), st), "gpx_append_row")
             check(lib.gpx_set_mask(dev.h, ptr(self.mask), ptr(self.loc2), 1, st), "gpx_set_mask")
@@ -929,7 +968,7 @@ class ShardedMIEngine(_Pivoting):
     def step(self):
         self.score()
         if self.score_trace is not None:
-            self.score_trace.append(self.scores[: self.hi - self.lo].cpu().numpy().copy())
+            self.score_trace.append(self.global_scores())
         self.take()
 
     def run(self, n_points: int, start: int = 0):

@@ -116,7 +116,7 @@ def _mi_evaluate(self, index, indexAdded):
         for i in added[len(st["prefix"]):]:
             eng.force(i)
         eng.score()
-        st.update(prefix=added, scores=eng.scores[: eng.pool.n].cpu().numpy())
+        st.update(prefix=added, scores=eng.global_scores())
     return st["scores"][int(index): int(index) + 1].copy()
 
 

@@ -154,16 +154,23 @@ int gpx_dgemm_tn_sub(gpx_handle h, const double* A, int64_t lda, const double* B
 int gpx_dgemm_tn_sub_padded(gpx_handle h, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                             int64_t ldc, int64_t I, int64_t J, int64_t K, int upper_only, void* stream);
 
+/* The padded update for an operand B that is one rank's column slice of a LOWER-triangular matrix (B[k, c] = 0 for
+ * k < global(c)) in a block-cyclic column distribution: local column j belongs to global block (j / blk) * world + rank.
+ * The structurally-zero leading rows of every 128-column tile are skipped (the Y = U^-T half of the MI set-up executes
+ * V^3/3 flop instead of 2 V^3/3).  blk: a multiple of 128. */
+int gpx_dgemm_tn_sub_lower(gpx_handle h, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                           int64_t I, int64_t J, int64_t K, int blk, int world, int rank, void* stream);
+
 /* Pivot record: what one greedy step needs to know about the chosen point.  Layout (doubles):
  *   [0] score  [1] global index (exact integer < 2^53)  [2] var_D(p) + noise (the squared divisor)
  *   [3 .. 3+GPX_MAX_DIM) coordinates of x_p   [GPX_PIVOT_HDR .. GPX_PIVOT_HDR + n) column W[0..n, p]   */
 #define GPX_PIVOT_HDR (3 + GPX_MAX_DIM)
 
 /* Fill a pivot record from the local candidate `*idx_dev` (device int64, local index):
- *     rec[1] = *idx_dev + index_offset, rec[0] = *score_dev. */
+ *     rec[1] = index_map ? index_map[*idx_dev] : *idx_dev + index_offset (the GLOBAL index), rec[0] = *score_dev. */
 int gpx_gather_pivot(gpx_handle h, const double* W, int64_t ldw, int64_t n, const double* var, const double* X,
                      int64_t ldx, const double* score_dev, const int64_t* idx_dev, int64_t index_offset,
-                     double noise, double* rec, void* stream);
+                     const int64_t* index_map, double noise, double* rec, void* stream);
 
 /* Pick the winning record among `nrec` records spaced `stride` doubles apart (NCCL all-gather output):
  * lowest score if minimize else highest, ties -> lowest global index (np.argmax / np.argmin order). */
@@ -230,10 +237,13 @@ int gpx_score_mi(gpx_handle h, const double* num_var, const double* prec_diag, d
 /* K6  column p of P = Y^T Y for the lower-triangular Y = U^-T:  out[i] = sum_{k >= max(i,p)} Y[k,i] Y[k,p].
  *     Y is nrows x ncols (row-major): the whole matrix (col_offset = 0, ncols = nrows, ycol = NULL) or the column slice
  *     [col_offset, col_offset+ncols) owned by this rank, in which case column p arrives as the dense vector ycol[nrows]
- *     (all-reduced from its owner).  *p_dev is the GLOBAL index.  workspace: gpx_mi_prec_column_workspace doubles. */
+ *     (all-reduced from its owner).  *p_dev is the GLOBAL index.  workspace: gpx_mi_prec_column_workspace doubles.
+ *     cyclic_blk > 0: the slice is block-cyclic instead of contiguous -- local column i is global column
+ *     ((i / blk) * cyclic_world + col_offset) * blk + i % blk, col_offset being the rank; blk a multiple of 256. */
 int64_t gpx_mi_prec_column_workspace(int64_t nrows, int64_t ldy);
 int gpx_mi_prec_column(gpx_handle h, const double* Y, int64_t nrows, int64_t ncols, int64_t ldy, int64_t col_offset,
-                       const int64_t* p_dev, const double* ycol, double* workspace, double* out, void* stream);
+                       int64_t cyclic_blk, int64_t cyclic_world, const int64_t* p_dev, const double* ycol, double* workspace,
+                       double* out, void* stream);
 
 /* Sharded pools: copy column *idx_dev of W (n rows) into rec[GPX_PIVOT_HDR..] and var[*idx_dev] into rec[2];
  * nothing is written when *idx_dev < 0, so zeroed records can be summed across ranks (owner contributes). */
@@ -243,6 +253,11 @@ int gpx_gather_column(gpx_handle h, const double* W, int64_t ldw, int64_t n, con
 /* out2[0] = local index of the pivot in rec (global index rec[1]) for the block [offset, offset+count), or -1;
  * out2[1] = the global index. */
 int gpx_local_index(gpx_handle h, const double* rec, int64_t offset, int64_t count, int64_t* out2, void* stream);
+/* the same for a block-cyclic distribution (global g on rank (g / blk) % world at ((g / blk) / world) * blk + g % blk) */
+int gpx_local_index_cyclic(gpx_handle h, const double* rec, int64_t blk, int64_t world, int64_t rank, int64_t count,
+                           int64_t* out2, void* stream);
+/* A[rows[j] * ld + j] += value, j < n (nugget / identity on the diagonal of a scattered column subset) */
+int gpx_add_at_rows(gpx_handle h, double* A, int64_t ld, const int64_t* rows, int64_t n, double value, void* stream);
 
 /* Column sums of squares: out[j] = sum_{i<n} W[i,j]^2 (optionally out[j] = base[j] - that). */
 int gpx_colsumsq(gpx_handle h, const double* W, int64_t n, int64_t ncols, int64_t ldw, const double* base,

@@ -66,7 +66,8 @@ if rank == 0:
            "design_s": design_s, "ms_per_step": 1e3 * design_s / (N - 1), "candidates_per_s_per_step": (N - 1) * V / design_s,
            "potrf_info": info, "distinct_picks": len(set(int(i) for i in idx)) == N, "first_picks": [int(i) for i in idx[:10]],
            "min_pick_score": float(scores[1:].min()), "max_pick_score": float(scores[1:].max()),
-           "hbm_per_gpu_gb": 2 * 8.0 * V * ((V + world - 1) // world) / 1e9}
+           "hbm_per_gpu_gb": 2 * 8.0 * V * max(eng.ncols_per_rank) / 1e9, "blk": eng.BLK,
+           "distribution": "block-cyclic column blocks, structural zeros of Y skipped in-kernel"}
     if args.compare_dense:
         dense = GreedyMIEngine(dev, dev.points(pool), N, noise)
         didx = dense.run(N, start=0)

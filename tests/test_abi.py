@@ -162,6 +162,21 @@ def test_host_logic_splits_and_scales():
         assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
         sizes = [b - a for a, b in blocks]
         assert max(sizes) - min(sizes) <= 1
+    # block-cyclic ownership of the MI factor columns: global g on rank (g // B) % world at ((g // B) // world) * B + g % B
+    from gpexp_b200.engine import ShardedMIEngine
+    for V, B, world in [(1000, 256, 3), (2048, 256, 8), (100, 256, 2), (5000, 512, 4)]:
+        seen = np.zeros(V, dtype=int)
+        for rank in range(world):
+            cols = ShardedMIEngine.cyclic_columns(V, B, world, rank)
+            seen[cols] += 1
+            assert np.all(np.diff(cols) > 0)
+            for loc in (0, len(cols) // 2, len(cols) - 1):
+                if len(cols):
+                    assert ShardedMIEngine.cyclic_local(int(cols[loc]), V, B, world, rank) == loc
+            other = (rank + 1) % world
+            if world > 1 and len(cols):
+                assert ShardedMIEngine.cyclic_local(int(cols[0]), V, B, world, other) == -1
+        assert np.all(seen == 1)
     assert prior_scale(_lib.SE, [0.1, 0.2, 3.0]) == 3.0
     assert prior_scale(_lib.MATERN32, [0.5, 2.0]) == 2.0
     assert abs(prior_scale(_lib.MEHLER, [0.6, 0.8]) - (1 / 0.8) * (1 / 0.6)) < 1e-15

@@ -1143,3 +1143,38 @@ def test_mi_cost_function_caches_the_factorisation(gx, golden):
     cf.add_candidates(len(pool) - 5, pool[:-5])
     cf.evaluate(0, [3])
     assert id(cf._mi_cache["engine"]) not in engines and cf._mi_cache["engine"].V == len(pool) - 5
+
+
+def test_dgemm_tn_sub_lower_skips_only_structural_zeros(gx):
+    """gpx_dgemm_tn_sub_lower (the Y = U^-T half of the MI set-up): B is one rank's block-cyclic column slice of a
+    lower-triangular matrix; skipping the rows above each tile's global column must not change the product."""
+    dev, lib, ptr = gx.dev, gx.lib, gx.ptr
+    rng = np.random.default_rng(17)
+    V, B, world = 2304, 256, 3
+    full = np.tril(rng.standard_normal((V, V)))                     # lower triangular V x V
+    K, I = 1800, 256                                                # contraction over the first K rows, I output rows
+    A = rng.standard_normal((K, I))
+    for rank in range(world):
+        blocks = list(range(rank, V // B, world))
+        gcols = np.concatenate([np.arange(g * B, (g + 1) * B) for g in blocks])
+        Bloc = full[:K, gcols]                                      # local slice (K x nloc)
+        nloc = gcols.size
+        ld = gx.device.roundup(nloc)
+        Ad = dev.zeros(K, 256)
+        Ad[:, :I] = dev.upload(A)
+        Bd = dev.zeros(K, ld)
+        Bd[:, :nloc] = dev.upload(Bloc)
+        C0 = rng.standard_normal((I, nloc))
+        outs = []
+        for lower in (False, True):
+            Cd = dev.zeros(I, ld)
+            Cd[:, :nloc] = dev.upload(C0)
+            if lower:
+                gx.check(lib.gpx_dgemm_tn_sub_lower(dev.h, ptr(Ad), 256, ptr(Bd), ld, ptr(Cd), ld, I, nloc, K, B, world, rank,
+                                                    dev.stream))
+            else:
+                gx.check(lib.gpx_dgemm_tn_sub_padded(dev.h, ptr(Ad), 256, ptr(Bd), ld, ptr(Cd), ld, I, nloc, K, 0, dev.stream))
+            outs.append(Cd[:, :nloc].cpu().numpy())
+        ref = C0 - A.T @ Bloc
+        assert np.max(np.abs(outs[0] - ref)) <= 1e-11 * np.max(np.abs(ref))
+        assert np.max(np.abs(outs[1] - ref)) <= 1e-11 * np.max(np.abs(ref)), rank
