@@ -62,7 +62,7 @@ scores = eng.pick_scores[:N].cpu().numpy()
 if rank == 0:
     out = {"workload": "cfg-4: 3-D Mehler t=0.9, greedy MI design of %d points from |V|=%d, noise 1e-2" % (N, V),
            "n_gpus": world, "setup_s": setup_s, "setup_useful_tflops_total": (2.0 * V ** 3 / 3.0) / setup_s / 1e12,
-           "setup_executed_tflops_per_gpu": (1.0 * V ** 3 / world) / setup_s / 1e12,
+           "setup_tflops_per_gpu": (2.0 * V ** 3 / 3.0 / world) / setup_s / 1e12,
            "design_s": design_s, "ms_per_step": 1e3 * design_s / (N - 1), "candidates_per_s_per_step": (N - 1) * V / design_s,
            "potrf_info": info, "distinct_picks": len(set(int(i) for i in idx)) == N, "first_picks": [int(i) for i in idx[:10]],
            "min_pick_score": float(scores[1:].min()), "max_pick_score": float(scores[1:].max()),
