@@ -49,7 +49,7 @@ extern "C" int gpx_prior_diag(gpx_handle h, const double* X, int64_t n, int64_t 
 #define GRAM_ROWS 16
 
 template <int FAM, int D>
-__global__ void __launch_bounds__(256) gram_kernel(const __grid_constant__ KParams kp, const double* __restrict__ X,
+__global__ void __launch_bounds__(256, 1) gram_kernel(const __grid_constant__ KParams kp, const double* __restrict__ X,
                                                     int64_t nx, int64_t ldx, const double* __restrict__ Y, int64_t ny,
                                                     int64_t ldy, double* __restrict__ out, int64_t ld, int add_diag,
                                                     const double* __restrict__ nugvec, double nug, int vec2) {
@@ -73,7 +73,10 @@ __global__ void __launch_bounds__(256) gram_kernel(const __grid_constant__ KPara
         __syncthreads();
         if (j < ny) {
             const int rows = (nx - i0) < GRAM_ROWS ? (int)(nx - i0) : GRAM_ROWS;
-#pragma unroll 4
+            // rows in flight per thread: 4 for small d; fewer once 2*D coordinates + D-term sums fill the register file
+            // (the Mehler instantiations at d >= 7 spilled with a fixed unroll of 4)
+            constexpr int RU = D <= 4 ? 4 : (D <= 8 ? 2 : 1);
+#pragma unroll RU
             for (int r = 0; r < rows; ++r) {
                 const int64_t row = i0 + r;
                 double a0 = 0.0, a1 = 0.0;

@@ -18,7 +18,7 @@
 #define MV_SPLITS_MAX 64
 
 template <int FAM, int D>
-__global__ void __launch_bounds__(128) gram_matvec_kernel(const __grid_constant__ KParams kp, const double* __restrict__ X,
+__global__ void __launch_bounds__(128, 1) gram_matvec_kernel(const __grid_constant__ KParams kp, const double* __restrict__ X,
                                                            int64_t n, int64_t ldx, const double* __restrict__ Y, int64_t m,
                                                            int64_t ldy, const double* __restrict__ b, int64_t cols_per_split,
                                                            double* __restrict__ part, int64_t ldp) {
