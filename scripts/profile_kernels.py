@@ -38,8 +38,8 @@ def ev_ms(fn, reps):
 
 
 # ceilings measured here: device copy (read + write) and pure streaming write
-buf = torch.empty(400_000_000, dtype=torch.float64, device="cuda")
-src = torch.empty(400_000_000, dtype=torch.float64, device="cuda")
+buf = torch.empty(4096 * 100_096, dtype=torch.float64, device="cuda")
+src = torch.empty(4096 * 100_096, dtype=torch.float64, device="cuda")
 t = ev_ms(lambda: buf.copy_(src), 5)
 out["copy_gbs"] = 2 * buf.numel() * 8 / t / 1e6
 t = ev_ms(lambda: buf.fill_(1.0), 5)

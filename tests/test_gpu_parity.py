@@ -267,7 +267,7 @@ def test_potrf_trsm_blocks(gx, n):
     p = dev.upload(np.array([n // 2], dtype=np.int64), dtype=gx.torch.int64)
     col = dev.zeros(ld)
     ws = dev.zeros(max(int(lib.gpx_mi_prec_column_workspace(n, ld)), 1))
-    gx.check(lib.gpx_mi_prec_column(dev.h, ptr(Y), n, n, ld, 0, ptr(p), None, ptr(ws), ptr(col), dev.stream))
+    gx.check(lib.gpx_mi_prec_column(dev.h, ptr(Y), n, n, ld, 0, 0, 1, ptr(p), None, ptr(ws), ptr(col), dev.stream))
     np.testing.assert_allclose(col[:n].cpu().numpy(), np.linalg.inv(A)[:, n // 2], rtol=1e-7, atol=1e-9)
     # rank-1 append reproduces the factor of the bordered matrix
     if n >= 2:
