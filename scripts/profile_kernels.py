@@ -56,6 +56,15 @@ for name, kern, d in [("se_2d", kernels.KernelSquaredExponential([0.06, 0.09], 1
     G = buf[: nx * X.ld].view(nx, X.ld)
     t = ev_ms(lambda: check(lib.gpx_gram(dev.h, ptr(X.X), nx, X.ld, ptr(X.X), X.n, X.ld, ptr(G), X.ld, 0, None, 0.0, dev.stream)), 5)
     out[f"gram_{name}_gbs"] = 8.0 * nx * C / t / 1e6
+    # the same block as a tensor-pipe Gram: DMMA prologue (expanded form) + store epilogue, no contraction (n = 0)
+    from gpexp_b200.device import prologue_operands
+    R = dev.points(rng.uniform(-1, 1, (nx, d)))
+    dev.set_center(X.midrange())
+    mode, ra, rb = prologue_operands(R, X)
+    t = ev_ms(lambda: check(lib.gpx_cov_from_factors(dev.h, mode, None, R.ld, ptr(ra), nx, None, X.ld, ptr(rb), C, 0, ptr(G), X.ld,
+                                                     dev.stream)), 5)
+    out[f"gram_dmma_{name}_gbs"] = 8.0 * nx * C / t / 1e6
+    out[f"gram_dmma_{name}_mode"] = int(mode)
     if once and name != "se_2d":
         continue
     # fused Gram/TRSM: W = U^-T K(D, X) for a 1024-point design (potrf + dmma_core<STORE> + tri_solve)
