@@ -48,11 +48,14 @@ extern "C" int gpx_prior_diag(gpx_handle h, const double* X, int64_t n, int64_t 
 // ---------------------------------------------------------------------------------------------
 #define GRAM_ROWS 16
 
-template <int FAM, int D>
+// per-dimension weight folded into the coordinates of the SE instantiation: (x - y)^2 a/2 * 256/ln2 = ((x - y) w)^2
+__device__ __forceinline__ double gram_se_weight(const KParams& kp, int q) { return sqrt(kp.a[q] * (0.5 * 0x1.71547652b82fep+8)); }
+
+template <int FAM, int D, bool DIAG>
 __global__ void __launch_bounds__(256, 1) gram_kernel(const __grid_constant__ KParams kp, const double* __restrict__ X,
-                                                    int64_t nx, int64_t ldx, const double* __restrict__ Y, int64_t ny,
-                                                    int64_t ldy, double* __restrict__ out, int64_t ld, int add_diag,
-                                                    const double* __restrict__ nugvec, double nug, int vec2) {
+                                                       int64_t nx, int64_t ldx, const double* __restrict__ Y, int64_t ny,
+                                                       int64_t ldy, double* __restrict__ out, int64_t ld,
+                                                       const double* __restrict__ nugvec, double nug, int vec2) {
     __shared__ double sx[D][GRAM_ROWS];
     __shared__ double s_tab[256];
     s_tab[threadIdx.x] = kp.signal * gpx_exp2_tab[threadIdx.x];
@@ -61,33 +64,47 @@ __global__ void __launch_bounds__(256, 1) gram_kernel(const __grid_constant__ KP
     double y0[D], y1[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-        y0[i] = (j < ny) ? Y[i * ldy + j] : 0.0;
-        y1[i] = (j + 1 < ny) ? Y[i * ldy + j + 1] : 0.0;
+        const double w = FAM == GPX_SE ? gram_se_weight(kp, i) : 1.0;
+        y0[i] = (j < ny) ? Y[i * ldy + j] * w : 0.0;
+        y1[i] = (j + 1 < ny) ? Y[i * ldy + j + 1] * w : 0.0;
     }
     for (int64_t i0 = (int64_t)blockIdx.y * GRAM_ROWS; i0 < nx; i0 += (int64_t)gridDim.y * GRAM_ROWS) {
         __syncthreads();
         if (threadIdx.x < GRAM_ROWS * D) {
             const int i = threadIdx.x / GRAM_ROWS, r = threadIdx.x % GRAM_ROWS;
-            sx[i][r] = (i0 + r < nx) ? X[i * ldx + i0 + r] : 0.0;
+            const double w = FAM == GPX_SE ? gram_se_weight(kp, i) : 1.0;
+            sx[i][r] = (i0 + r < nx) ? X[i * ldx + i0 + r] * w : 0.0;
         }
         __syncthreads();
         if (j < ny) {
             const int rows = (nx - i0) < GRAM_ROWS ? (int)(nx - i0) : GRAM_ROWS;
             // rows in flight per thread: 4 for small d; fewer once 2*D coordinates + D-term sums fill the register file
-            // (the Mehler instantiations at d >= 7 spilled with a fixed unroll of 4)
             constexpr int RU = D <= 4 ? 4 : (D <= 8 ? 2 : 1);
 #pragma unroll RU
             for (int r = 0; r < rows; ++r) {
                 const int64_t row = i0 + r;
                 double a0 = 0.0, a1 = 0.0;
+                double v0, v1;
+                if (FAM == GPX_SE) {
+                    // weighted coordinates: one subtraction and one FMA per dimension, exponent already in table units
 #pragma unroll
-                for (int i = 0; i < D; ++i) {
-                    kacc_dim<FAM>(a0, kp, i, sx[i][r], y0[i]);
-                    kacc_dim<FAM>(a1, kp, i, sx[i][r], y1[i]);
+                    for (int i = 0; i < D; ++i) {
+                        const double d0 = sx[i][r] - y0[i], d1 = sx[i][r] - y1[i];
+                        a0 = fma(d0, d0, a0);
+                        a1 = fma(d1, d1, a1);
+                    }
+                    v0 = gpx_exp_tab_scaled(a0, s_tab);
+                    v1 = gpx_exp_tab_scaled(a1, s_tab);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+                        kacc_dim<FAM>(a0, kp, i, sx[i][r], y0[i]);
+                        kacc_dim<FAM>(a1, kp, i, sx[i][r], y1[i]);
+                    }
+                    v0 = kfinish_tab<FAM>(a0, kp, s_tab);
+                    v1 = kfinish_tab<FAM>(a1, kp, s_tab);
                 }
-                double v0 = kfinish_tab<FAM>(a0, kp, s_tab);
-                double v1 = kfinish_tab<FAM>(a1, kp, s_tab);
-                if (add_diag) {
+                if (DIAG) {
                     if (row == j) v0 += nugvec ? nugvec[row] : nug;
                     if (row == j + 1) v1 += nugvec ? nugvec[row] : nug;
                 }
@@ -114,8 +131,13 @@ extern "C" int gpx_gram(gpx_handle h, const double* X, int64_t nx, int64_t ldx, 
     if (gy > 32768) gy = 32768;
     dim3 grid((unsigned)((ny + 511) / 512), (unsigned)gy);
     const int vec2 = ((ld & 1) == 0 && gpx_aligned16(out)) ? 1 : 0;
-    GPX_DISPATCH_FAMILY(h->kp.family, GPX_DISPATCH_DIM(h->kp.d, (gram_kernel<FAM, D><<<grid, 256, 0, st>>>(
-                                                                    h->kp, X, nx, ldx, Y, ny, ldy, out, ld, add_diag, nugget_vec, nugget, vec2))));
+    if (add_diag) {
+        GPX_DISPATCH_FAMILY(h->kp.family, GPX_DISPATCH_DIM(h->kp.d, (gram_kernel<FAM, D, true><<<grid, 256, 0, st>>>(
+                                                                        h->kp, X, nx, ldx, Y, ny, ldy, out, ld, nugget_vec, nugget, vec2))));
+    } else {
+        GPX_DISPATCH_FAMILY(h->kp.family, GPX_DISPATCH_DIM(h->kp.d, (gram_kernel<FAM, D, false><<<grid, 256, 0, st>>>(
+                                                                        h->kp, X, nx, ldx, Y, ny, ldy, out, ld, nugget_vec, nugget, vec2))));
+    }
     return gpx_check_launch("gpx_gram");
 }
 

@@ -132,6 +132,25 @@ __device__ __forceinline__ double gpx_exp_tab(double x, const double* __restrict
     return n < -261632 ? 0.0 : res;                             // below 2^-1022: flush (x < -708.4)
 }
 
+// exp(-S * ln2/256) for an exponent that was accumulated ALREADY SCALED by 256/ln2 (S >= 0): the SE Gram kernel folds
+// sqrt(a_q/2 * 256/ln2) into its coordinates, so that S = sum ((x_q - y_q) w_q)^2 costs two FP64 operations per dimension
+// and the argument scaling of gpx_exp_tab disappears.  Same table, same polynomial.
+__device__ __forceinline__ double gpx_exp_tab_scaled(double S, const double* __restrict__ tab) {
+    const double MAGIC = 6755399441055744.0;                    // 1.5 * 2^52
+    const double t = MAGIC - S;                                 // -rint(S) in the low word
+    const int n = __double2loint(t);
+    const double nf = t - MAGIC;                                // = -rint(S), exact
+    const double r = (S + nf) * -0x1.62e42fefa39efp-9;          // (rint(S) - S) * ln2/256 : |S + nf| <= 1/2, exact sum
+    double p = fma(1.0 / 24.0, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    const double q = p * r;                                     // e^r - 1
+    const double tj = tab[n & 255];
+    double res = fma(tj, q, tj);
+    res = __hiloint2double(__double2hiint(res) + ((n >> 8) << 20), __double2loint(res));  // * 2^k
+    return n < -261632 ? 0.0 : res;                             // below 2^-1022: flush
+}
+
 // difference-form finish with the table exp; `tab` already carries the signal variance (tab[j] = signal * 2^(j/256))
 template <int FAM>
 __device__ __forceinline__ double kfinish_tab(double acc, const KParams& kp, const double* __restrict__ tab) {
