@@ -51,6 +51,51 @@ extern "C" int gpx_prior_diag(gpx_handle h, const double* X, int64_t n, int64_t 
 // per-dimension weight folded into the coordinates of the SE instantiation: (x - y)^2 a/2 * 256/ln2 = ((x - y) w)^2
 __device__ __forceinline__ double gram_se_weight(const KParams& kp, int q) { return sqrt(kp.a[q] * (0.5 * 0x1.71547652b82fep+8)); }
 
+// GRAM_ROWS (or fewer) rows of two adjacent columns: covariance, optional nugget on the diagonal, streaming stores
+template <int FAM, int D, bool DIAG, bool PAIR>
+__device__ __forceinline__ void gram_rows(const KParams& kp, const double (&sx)[D][GRAM_ROWS], const double (&y0)[D],
+                                          const double (&y1)[D], const double* __restrict__ s_tab, int rows, int64_t i0,
+                                          int64_t j, double* __restrict__ dst, int64_t ld, const double* __restrict__ nugvec,
+                                          double nug, bool second = true) {
+    // rows in flight per thread: 4 for small d; fewer once 2*D coordinates + D-term sums fill the register file
+    constexpr int RU = D <= 4 ? 4 : (D <= 8 ? 2 : 1);
+#pragma unroll RU
+    for (int r = 0; r < rows; ++r, dst += ld) {
+        double a0 = 0.0, a1 = 0.0;
+        double v0, v1;
+        if (FAM == GPX_SE) {
+            // weighted coordinates: one subtraction and one FMA per dimension, exponent already in table units
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                const double d0 = sx[i][r] - y0[i], d1 = sx[i][r] - y1[i];
+                a0 = fma(d0, d0, a0);
+                a1 = fma(d1, d1, a1);
+            }
+            v0 = gpx_exp_tab_scaled(a0, s_tab);
+            v1 = gpx_exp_tab_scaled(a1, s_tab);
+        } else {
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                kacc_dim<FAM>(a0, kp, i, sx[i][r], y0[i]);
+                kacc_dim<FAM>(a1, kp, i, sx[i][r], y1[i]);
+            }
+            v0 = kfinish_tab<FAM>(a0, kp, s_tab);
+            v1 = kfinish_tab<FAM>(a1, kp, s_tab);
+        }
+        if (DIAG) {
+            const int64_t row = i0 + r;
+            if (row == j) v0 += nugvec ? nugvec[row] : nug;
+            if (row == j + 1) v1 += nugvec ? nugvec[row] : nug;
+        }
+        if (PAIR) {
+            __stcs(reinterpret_cast<double2*>(dst), make_double2(v0, v1));
+        } else {
+            __stcs(dst, v0);
+            if (second) __stcs(dst + 1, v1);
+        }
+    }
+}
+
 template <int FAM, int D, bool DIAG>
 __global__ void __launch_bounds__(256, 1) gram_kernel(const __grid_constant__ KParams kp, const double* __restrict__ X,
                                                        int64_t nx, int64_t ldx, const double* __restrict__ Y, int64_t ny,
@@ -78,43 +123,12 @@ __global__ void __launch_bounds__(256, 1) gram_kernel(const __grid_constant__ KP
         __syncthreads();
         if (j < ny) {
             const int rows = (nx - i0) < GRAM_ROWS ? (int)(nx - i0) : GRAM_ROWS;
-            // rows in flight per thread: 4 for small d; fewer once 2*D coordinates + D-term sums fill the register file
-            constexpr int RU = D <= 4 ? 4 : (D <= 8 ? 2 : 1);
-#pragma unroll RU
-            for (int r = 0; r < rows; ++r) {
-                const int64_t row = i0 + r;
-                double a0 = 0.0, a1 = 0.0;
-                double v0, v1;
-                if (FAM == GPX_SE) {
-                    // weighted coordinates: one subtraction and one FMA per dimension, exponent already in table units
-#pragma unroll
-                    for (int i = 0; i < D; ++i) {
-                        const double d0 = sx[i][r] - y0[i], d1 = sx[i][r] - y1[i];
-                        a0 = fma(d0, d0, a0);
-                        a1 = fma(d1, d1, a1);
-                    }
-                    v0 = gpx_exp_tab_scaled(a0, s_tab);
-                    v1 = gpx_exp_tab_scaled(a1, s_tab);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < D; ++i) {
-                        kacc_dim<FAM>(a0, kp, i, sx[i][r], y0[i]);
-                        kacc_dim<FAM>(a1, kp, i, sx[i][r], y1[i]);
-                    }
-                    v0 = kfinish_tab<FAM>(a0, kp, s_tab);
-                    v1 = kfinish_tab<FAM>(a1, kp, s_tab);
-                }
-                if (DIAG) {
-                    if (row == j) v0 += nugvec ? nugvec[row] : nug;
-                    if (row == j + 1) v1 += nugvec ? nugvec[row] : nug;
-                }
-                double* dst = out + row * ld + j;
-                if (vec2 && j + 1 < ny) {
-                    __stcs(reinterpret_cast<double2*>(dst), make_double2(v0, v1));
-                } else {
-                    __stcs(dst, v0);
-                    if (j + 1 < ny) __stcs(dst + 1, v1);
-                }
+            double* dst = out + i0 * ld + j;
+            // the common case (aligned rows, both columns live) runs a branch-free loop with one 16-byte store per row
+            if (vec2 && j + 1 < ny) {
+                gram_rows<FAM, D, DIAG, true>(kp, sx, y0, y1, s_tab, rows, i0, j, dst, ld, nugvec, nug);
+            } else {
+                gram_rows<FAM, D, DIAG, false>(kp, sx, y0, y1, s_tab, rows, i0, j, dst, ld, nugvec, nug, j + 1 < ny);
             }
         }
     }
