@@ -75,7 +75,7 @@ SIGNATURES = {
     "gpx_chol_append": [_p, _p, _i64, _i64, _p, _dbl, _p, _p],
     "gpx_set_center": [_p, C.POINTER(_dbl)],
     "gpx_prep_side": [_p, _int, _p, _i64, _i64, _p, _i64, _p, _p],
-    "gpx_trsm_gram": [_p, _int, _p, _i64, _i64, _p, _i64, _p, _p, _i64, _i64, _p, _i64, _p, _p],
+    "gpx_trsm_gram": [_p, _p, _i64, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _p, _p],
     "gpx_trsm": [_p, _p, _i64, _i64, _p, _i64, _i64, _p],
     "gpx_trsm_back": [_p, _p, _i64, _i64, _p, _i64, _i64, _p],
     "gpx_trtri_t": [_p, _p, _i64, _i64, _p, _i64, _p],

@@ -6,8 +6,9 @@
 //       solve and rank-32 update by the whole CTA;
 //   (2) block row  U12 = U11^-T A12   : one thread per column, forward substitution, U11 in shared memory;
 //   (3) trailing   A22 -= U12^T U12   : DMMA core (gpx_dgemm_tn_sub, upper tiles only).
-// trsm (W = U^-T B), left-looking in 128-row blocks: DMMA core (K = rows already solved) + the same
-// forward-substitution kernel.  With the Gram prologue the right-hand side K(D,Y) is never materialised.
+// trsm (W = U^-T B), left-looking in 128-row blocks: DMMA update (K = rows already solved) + the same
+// forward-substitution kernel.  gpx_trsm_gram writes each 128-row block of the right-hand side K(D,Y) straight into W
+// (difference-form Gram kernel), so the n x ny Gram matrix never exists beside W.
 #include <math.h>
 
 #include "gpx_common.cuh"
@@ -196,23 +197,30 @@ extern "C" int gpx_potrf(gpx_handle h, double* A, int64_t n, int64_t ld, int* in
     return GPX_OK;
 }
 
-extern "C" int gpx_trsm_gram(gpx_handle h, int prologue, const double* U, int64_t n, int64_t ldu, const double* Da_rows,
-                             int64_t ldd, const double* Y, const double* Yb_rows, int64_t ny, int64_t ldy, double* W,
-                             int64_t ldw, double* var_out, void* stream) {
+extern "C" int gpx_trsm_gram(gpx_handle h, const double* U, int64_t n, int64_t ldu, const double* D, int64_t ldd,
+                             const double* Y, int64_t ny, int64_t ldy, double* W, int64_t ldw, double* var_out, void* stream) {
     GPX_NEED_KERNEL(h);
     GPX_REQUIRE(n >= 0 && ny >= 0, GPX_EINVAL, "negative size");
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     if (ny == 0) return GPX_OK;
     if (n > 0) {
-        GPX_REQUIRE(U && Da_rows && Yb_rows && W, GPX_EINVAL, "NULL pointer");
-        GPX_REQUIRE(ldd == ldu, GPX_EINVAL, "the prepared design side must share the leading dimension of U");
+        GPX_REQUIRE(U && D && Y && W, GPX_EINVAL, "NULL pointer");
+        // whole 128-wide tiles readable on both operands -> the TMA update kernel; else the predicated one
+        const bool padded = (ldu % NB) == 0 && ldu >= (n + NB - 1) / NB * NB && (ldw % NB) == 0 && ldw >= (ny + NB - 1) / NB * NB &&
+                            gpx_aligned16(U) && gpx_aligned16(W);
         for (int64_t kb = 0; kb < n; kb += NB) {
             const int b = (int)(n - kb < NB ? n - kb : NB);
-            // block row:  W[kb:kb+b, :] = K(D[kb:kb+b], Y) - U[0:kb, kb:kb+b]^T W[0:kb, :]
-            rc = gpx_launch_core_store(h, prologue, U + kb, ldu, Da_rows + kb, b, W, ldw, Yb_rows, ny, kb, W + kb * ldw, ldw,
-                                       st);
+            // block row:  W[kb:kb+b, :] = K(D[kb:kb+b], Y)            difference-form Gram, written once (8 b ny bytes)
+            rc = gpx_gram(h, D + kb, b, ldd, Y, ny, ldy, W + kb * ldw, ldw, 0, nullptr, 0.0, stream);
             if (rc) return rc;
+            //             W[kb:kb+b, :] -= U[0:kb, kb:kb+b]^T W[0:kb, :]  FP64 DMMA update
+            if (kb > 0) {
+                rc = padded ? gpx_dgemm_tn_sub_padded(h, U + kb, ldu, W, ldw, W + kb * ldw, ldw, b, ny, kb, 0, stream)
+                            : gpx_dgemm_tn_sub(h, U + kb, ldu, W, ldw, W + kb * ldw, ldw, b, ny, kb, 0, stream);
+                if (rc) return rc;
+            }
+            //             W[kb:kb+b, :] = U_kk^-T W[kb:kb+b, :]           forward substitution
             rc = launch_tri_solve<false>(h, U + kb * ldu + kb, ldu, b, W + kb * ldw, ldw, ny, st);
             if (rc) return rc;
         }

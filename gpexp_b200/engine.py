@@ -310,11 +310,8 @@ class DesignFactor:
         if W is None:
             W = dev.zeros(max(self.n, 1), X.ld)
         var = dev.zeros(X.ld) if want_var else None
-        if self.n:
-            dev.set_center(X.midrange())
-        mode, da_rows, xb_rows = prologue_operands(D, X) if self.n else (_lib.PRO_DIFF, D.X, X.X)
-        check(lib.gpx_trsm_gram(dev.h, mode, ptr(self.U), self.n, self.ldu, ptr(da_rows), D.ld, ptr(X.X), ptr(xb_rows), X.n,
-                                X.ld, ptr(W), X.ld, ptr(var), dev.stream), "gpx_trsm_gram")
+        check(lib.gpx_trsm_gram(dev.h, ptr(self.U), self.n, self.ldu, ptr(D.X), D.ld, ptr(X.X), X.n, X.ld, ptr(W), X.ld,
+                                ptr(var), dev.stream), "gpx_trsm_gram")
         return W, var
 
     def solve_vector(self, y: np.ndarray) -> np.ndarray:

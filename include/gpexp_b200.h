@@ -119,15 +119,14 @@ int gpx_set_center(gpx_handle h, const double* center_host);
 int gpx_prep_side(gpx_handle h, int side, const double* X, int64_t n, int64_t ldx, double* rows, int64_t ld,
                   double* maxabs, void* stream);
 
-/* K1+K3  W = U^-T K(D, Y) without materialising K(D,Y):  left-looking blocked TRSM whose block rows are
- *     produced by the DMMA contraction kernel with the Gram evaluated in its prologue.  Replaces
- *     np.dot(precision, kernelvals) at gp.py:253-255 / experimentalDesign.py:836-837.
- *     Da_rows / Yb_rows: per `prologue`, prepared sides (GPX_SIDE_A of the design, GPX_SIDE_B of the query points) or
- *     the raw coordinates; leading dimensions ldd == ldu and ldw.
+/* K1+K3  W = U^-T K(D, Y):  left-looking blocked TRSM whose 128-row blocks of the right-hand side are written straight
+ *     into W by the difference-form Gram kernel, updated by the FP64 DMMA routine (the TMA kernel when ldu, ldw are
+ *     multiples of 128 covering whole tiles -- zero-initialised padding --, else the predicated one) and finished by a
+ *     forward substitution.  Replaces np.dot(precision, kernelvals) at gp.py:253-255 / experimentalDesign.py:836-837.
+ *     D: design coordinates (d x ldd), Y: query coordinates (d x ldy).
  *     var_out (nullable): var[j] = k(y_j,y_j) - sum_i W[i,j]^2     (K4, a7 GP.evaluateVariance). */
-int gpx_trsm_gram(gpx_handle h, int prologue, const double* U, int64_t n, int64_t ldu, const double* Da_rows, int64_t ldd,
-                  const double* Y, const double* Yb_rows, int64_t ny, int64_t ldy, double* W, int64_t ldw, double* var_out,
-                  void* stream);
+int gpx_trsm_gram(gpx_handle h, const double* U, int64_t n, int64_t ldu, const double* D, int64_t ldd, const double* Y,
+                  int64_t ny, int64_t ldy, double* W, int64_t ldw, double* var_out, void* stream);
 
 /* In-place B <- U^-T B for a materialised right-hand side (n x ncols). */
 int gpx_trsm(gpx_handle h, const double* U, int64_t n, int64_t ldu, double* B, int64_t ncols, int64_t ldb,
