@@ -1178,3 +1178,53 @@ def test_dgemm_tn_sub_lower_skips_only_structural_zeros(gx):
         ref = C0 - A.T @ Bloc
         assert np.max(np.abs(outs[0] - ref)) <= 1e-11 * np.max(np.abs(ref))
         assert np.max(np.abs(outs[1] - ref)) <= 1e-11 * np.max(np.abs(ref)), rank
+
+
+def test_round2_abi_edge_cases(gx):
+    """Empty ranges, missing communicator, struct-size handshake and argument validation of the round-2 entry points."""
+    import ctypes as C
+    dev, lib, ptr, torch, L = gx.dev, gx.lib, gx.ptr, gx.torch, gx._lib
+    bind(gx, "se_ard_2d")
+    assert lib.gpx_state_bytes(0) == C.sizeof(L.IvarState) and lib.gpx_state_bytes(1) == C.sizeof(L.VarState)
+    assert lib.gpx_state_bytes(7) == -1
+    # collectives without gpx_comm_init answer GPX_ENOCOMM (-5), never crash
+    a = dev.zeros(8)
+    assert lib.gpx_comm_size(dev.h) in (0, 1) or lib.gpx_comm_size(dev.h) > 1
+    if lib.gpx_comm_size(dev.h) == 0:
+        assert lib.gpx_comm_allgather(dev.h, ptr(a), ptr(a), 4, dev.stream) == -5
+        assert "gpx_comm_init" in L.last_error()
+        assert lib.gpx_comm_bcast(dev.h, ptr(a), 4, 0, dev.stream) == -5
+    # ring selection is validated
+    assert lib.gpx_set_ivar_ring(dev.h, 3) == -1 and lib.gpx_set_ivar_ring(dev.h, 1) == 0
+    # an empty step range is a no-op; a range beyond the capacity is refused
+    rng = np.random.default_rng(2)
+    k = bind(gx, "se_ard_2d")
+    fam, d, params = k._gpx_spec()
+    eng = gx.engine.GreedyIVAREngine(dev, dev.points(rng.uniform(-1, 1, (300, 2))), dev.points(rng.uniform(-1, 1, (500, 2))), 4,
+                                     1e-6, gx.engine.prior_scale(fam, params))
+    st = eng._state()
+    assert lib.gpx_ivar_greedy_run(dev.h, C.byref(st), 0, 0, dev.stream) == 0
+    assert lib.gpx_ivar_greedy_run(dev.h, C.byref(st), 0, 5, dev.stream) == -1 and "capacity" in L.last_error()
+    assert lib.gpx_ivar_greedy_run(dev.h, None, 0, 1, dev.stream) == -1
+    eng.run(4)
+    assert len(set(int(i) for i in eng.indices())) == 4
+    # Gram x vector: empty sides
+    ws = dev.zeros(int(lib.gpx_gram_matvec_workspace(16)))
+    out = dev.zeros(16)
+    X = dev.points(rng.uniform(-1, 1, (16, 2)))
+    assert lib.gpx_gram_matvec(dev.h, ptr(X.X), 0, X.ld, ptr(X.X), 16, X.ld, ptr(a), ptr(ws), ptr(out), dev.stream) == 0
+    assert lib.gpx_gram_matvec(dev.h, ptr(X.X), 16, X.ld, None, 0, X.ld, None, ptr(ws), ptr(out), dev.stream) == 0
+    assert float(out.abs().max().item()) == 0.0
+    # the expanded form refuses d > 14 (the prepared side has d + 2 <= 16 rows); the difference form takes it
+    k16 = product_kernel("se_ard_10d")
+    from gpexp_b200 import kernels as K
+    k16 = K.KernelSquaredExponential(list(np.linspace(0.5, 1.5, 16)), 1.0, 16)
+    k16._bind(dev)
+    P = dev.points(rng.uniform(-1, 1, (130, 16)))
+    rows = dev.zeros(16, P.ld)
+    assert lib.gpx_prep_side(dev.h, 0, ptr(P.X), 130, P.ld, ptr(rows), P.ld, None, dev.stream) == -4   # GPX_ESIZE
+    from gpexp_b200.device import prologue_operands
+    assert prologue_operands(P, P)[0] == L.PRO_DIFF
+    # block-cyclic helpers validate their description
+    assert lib.gpx_dgemm_tn_sub_lower(dev.h, ptr(a), 128, ptr(a), 128, ptr(a), 128, 1, 1, 1, 100, 2, 0, dev.stream) == -1
+    assert lib.gpx_local_index_cyclic(dev.h, ptr(a), 256, 2, 2, 10, ptr(dev.zeros(2, dtype=torch.int64)), dev.stream) == -1
