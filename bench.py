@@ -12,7 +12,9 @@ inside the timed region).
 N > 1 is STRONG scaling: the same 100 000 candidates are split into N contiguous blocks (integration points replicated), one
 NCCL all-gather of pivot records per step.  Every N > 1 line also carries a `parity` block (sharded greedy IVAR / greedy
 variance / greedy MI on small seeded pools against the CPU oracle, all ranks agreeing) and, at N = 8, `extras.cfg5`: the
-north-star step (10-D ARD, n = 4096, 1 000 000 candidates x 100 000 MC points).
+north-star step (10-D ARD, n = 4096, 1 000 000 candidates x 100 000 MC points).  The other BASELINE configurations ride in
+`extras` of every line: cfg-1 (N = 1), cfg-3 (whole 1 024-point conditional-entropy design from 250 000 candidates) and
+cfg-4 (512-point MI design; pool 40 000 / 80 000 / 120 000 / 200 000 on 1 / 2 / 4 / 8 GPUs).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
@@ -326,6 +328,80 @@ def cfg5_block(ed, gpmod, kernels, Space, shard, dist, torch, rank, world, local
     return out
 
 
+def cfg3_block(ed, kernels, shard, dist, torch, rank, world):
+    """BASELINE configs[2]: 5-D Matern, conditional-entropy greedy design of 1 024 points from 250 000 candidates (the pool
+    sharded over the ranks), through performGreedyVarExperimentalDesign -> gpx_var_greedy_run."""
+    rng = np.random.default_rng(3)
+    C, N = 250_000, 1024
+    pool = rng.uniform(-1, 1, (C, 5))
+    kern = kernels.KernelIsoMatern(1.0, 1.0, 5)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    ed.performGreedyVarExperimentalDesign(kern, pool[:5000], 16, 5, shard=shard)     # warm-up (allocator, communicator)
+    sync()
+    t0 = time.perf_counter()
+    pts = ed.performGreedyVarExperimentalDesign(kern, pool, N, 5, shard=shard)
+    sync()
+    t = time.perf_counter() - t0
+    if rank != 0:
+        return None
+    bytes_alg = sum(8.0 * (n + 2) * C for n in range(N))
+    out = {"workload": f"cfg-3: 5-D Matern rho=1, greedy max posterior variance, 1 024 of 250 000 candidates, candidates/{world}",
+           "design_s": t, "candidates_per_s_per_step": N * C / t, "append_gbs_aggregate": bytes_alg / t / 1e9,
+           "call": "performGreedyVarExperimentalDesign(kernel, pool, 1024, 5, shard) from host arrays (upload included)"}
+    # checker: first 150 picks against the oracle, all picks distinct
+    from oracle import gpexp_oracle as orc
+    ref, _ = orc.fast_greedy_var(orc.KernelSpec.matern32(1.0, 1.0, 5), pool, 150)
+    out["first_150_picks_match_oracle"] = bool(np.array_equal(pts[:150], pool[ref]))
+    out["distinct_points"] = bool(len(np.unique(pts, axis=0)) == N)
+    return out
+
+
+def cfg4_block(ed, gpmod, kernels, Space, shard, dist, torch, rank, world):
+    """BASELINE configs[3]: 3-D Mehler, greedy mutual-information design of 512 points; the |V| x |V| factor and its
+    inverse-transpose are sharded block-cyclically, so the pool size follows the memory of the job:
+    |V| = 40 000 / 80 000 / 120 000 / 200 000 (the full cfg-4 size) on 1 / 2 / 4 / 8 GPUs."""
+    V = {1: 40_000, 2: 80_000, 4: 120_000}.get(world, 200_000 if world >= 8 else 40_000 * world)
+    N, noise = 512, 1e-2
+    pool = np.random.default_rng(4).standard_normal((V, 3))
+    kern = kernels.KernelMehlerND([0.9, 0.9, 0.9], 3)
+    from gpexp_b200.engine import ShardedMIEngine
+    from gpexp_b200.device import Device
+    dev = Device.get()
+    kern._bind(dev)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    sync()
+    t0 = time.perf_counter()
+    eng = ShardedMIEngine(dev, pool, N, noise, shard=shard)
+    sync()
+    setup_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    idx = eng.run(N, start=0)
+    sync()
+    design_s = time.perf_counter() - t0
+    info = int(eng.info.item())
+    out = None
+    if rank == 0:
+        out = {"workload": f"cfg-4: 3-D Mehler t=0.9, greedy MI design of 512 points from |V|={V}, noise 1e-2, "
+                           f"block-cyclic column blocks over {world} GPU(s)" + ("" if V == 200_000 else " (full cfg-4 size is 200 000 on 8 GPUs)"),
+               "V": V, "setup_s": setup_s, "setup_tflops_per_gpu": (2.0 * V ** 3 / 3.0 / world) / setup_s / 1e12,
+               "design_s": design_s, "ms_per_step": 1e3 * design_s / (N - 1), "candidates_per_s_per_step": (N - 1) * V / design_s,
+               "potrf_info": info, "distinct_picks": len(set(int(i) for i in idx)) == N, "first_picks": [int(i) for i in idx[:8]],
+               "hbm_per_gpu_gb": 2 * 8.0 * V * max(eng.ncols_per_rank) / 1e9, "blk": eng.BLK}
+    del eng
+    torch.cuda.empty_cache()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
@@ -467,6 +543,10 @@ def run_ours(args):
         parity = parity_block(ed, gpmod, kernels, Space, ShardedMIEngine, Device, shard, dist, torch, rank, world)
     if world >= 8 and not args.no_cfg5:
         cfg5 = cfg5_block(ed, gpmod, kernels, Space, shard, dist, torch, rank, world, local, dgemm_tflops)
+    cfg3 = cfg4 = None
+    if not args.no_configs:
+        cfg3 = cfg3_block(ed, kernels, shard, dist, torch, rank, world)
+        cfg4 = cfg4_block(ed, gpmod, kernels, Space, shard, dist, torch, rank, world)
 
     if rank != 0:
         if world > 1:
@@ -643,6 +723,10 @@ def run_ours(args):
                   "hbm_peak_source": hbm_src}
     if cfg5 is not None:
         extras["cfg5"] = cfg5
+    if cfg3 is not None:
+        extras["cfg3"] = cfg3
+    if cfg4 is not None:
+        extras["cfg4"] = cfg4
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -679,6 +763,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-parity", action="store_true", help="skip the N>1 parity block")
     ap.add_argument("--no-cfg5", action="store_true", help="skip extras.cfg5 at N=8")
+    ap.add_argument("--no-configs", action="store_true", help="skip extras.cfg3 / extras.cfg4 (the other BASELINE configurations)")
     ap.add_argument("--quick-design", action="store_true",
                     help="profiling aid: load a random 255-point design instead of running the 255 greedy steps")
     args = ap.parse_args()

@@ -17,7 +17,10 @@
  *     never synchronise the device unless stated;
  *   - return value: 0 = OK, <0 = bad argument (GPX_E*), >0 = cudaError_t of a failed launch;
  *     gpx_last_error() returns a thread-local host string;
- *   - no exceptions, no exit(), re-entrant per handle, one handle per device.
+ *   - no exceptions, no exit(), re-entrant per handle, one handle per device;
+ *   - a handle's calls share its reduction scratch (arg-reduce / sum tickets and partials): issue them on ONE stream at
+ *     a time; use a second handle (gpx_create on the same device) for a second concurrent stream or host thread;
+ *   - shared-memory opt-ins are tracked per handle, i.e. per device.
  */
 #ifndef GPEXP_B200_H
 #define GPEXP_B200_H
