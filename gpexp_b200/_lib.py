@@ -89,7 +89,7 @@ SIGNATURES = {
     "gpx_set_ivar_ring": [_p, _int],
     "gpx_score_ivar_workspace": [_p, _i64, _i64],
     "gpx_score_ivar": [_p, _int, _p, _i64, _p, _p, _i64, _p, _i64, _p, _p, _i64, _i64, _dbl, _dbl, _p, _p, _p, _p, _p, _p],
-    "gpx_cov_segments": [_i64],
+    "gpx_cov_segments": [_i64, _i64],
     "gpx_cov_update": [_p, _p, _i64, _i64, _i64, _p, _p, _p, _i64, _p],
     "gpx_cov_from_factors": [_p, _int, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _p],
     "gpx_score_ivar_partials": [_p, _p, _int, _i64, _p, _i64, _p, _i64, _dbl, _dbl, _p, _p, _p, _p, _p],

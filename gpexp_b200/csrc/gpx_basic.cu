@@ -385,15 +385,15 @@ extern "C" int gpx_sum(gpx_handle h, const double* v, int64_t n, double* out, vo
 // K3+K4 incremental row append.  Two adjacent columns per thread (16-byte streaming loads), the pivot's
 // W-column in shared memory, 8 independent loads in flight per thread.  Reads 8*n*ncols bytes.
 // ---------------------------------------------------------------------------------------------
-template <int FAM, int SRC>
-__global__ void __launch_bounds__(128) append_row_kernel(const __grid_constant__ KParams kp, const double* __restrict__ rec,
+template <int FAM, int SRC, int NT>
+__global__ void __launch_bounds__(NT) append_row_kernel(const __grid_constant__ KParams kp, const double* __restrict__ rec,
                                                           const double* __restrict__ src_row, const double* __restrict__ Y,
                                                           int64_t ncols, int64_t ldy, double* __restrict__ W, int64_t ldw,
                                                           int n, double* __restrict__ var) {
     extern __shared__ double sl[];
-    for (int i = threadIdx.x; i < n; i += 128) sl[i] = rec[GPX_PIVOT_HDR + i];
+    for (int i = threadIdx.x; i < n; i += NT) sl[i] = rec[GPX_PIVOT_HDR + i];
     __syncthreads();
-    const int64_t j = ((int64_t)blockIdx.x * 128 + threadIdx.x) * 2;
+    const int64_t j = ((int64_t)blockIdx.x * NT + threadIdx.x) * 2;
     if (j >= ncols) return;
     const double* wp = W + j;
     double a0 = 0.0, a1 = 0.0;
@@ -473,14 +473,22 @@ extern "C" int gpx_append_row(gpx_handle h, int row_source, const double* rec, c
     const size_t smem = (size_t)n * sizeof(double);
     GPX_REQUIRE(smem <= 200 * 1024, GPX_ESIZE, "design size exceeds the shared-memory column buffer (25600)");
     cudaStream_t st = (cudaStream_t)stream;
-    const unsigned grid = (unsigned)((ncols + 255) / 256);
+    // 256 columns per 128-thread block; with fewer than ~6 such blocks per SM (C = 1e5: 2.6) the SMs are unevenly loaded
+    // and too few loads are in flight during the ramp, so narrow problems run 64-thread blocks of 128 columns
+    const int sms = h->sm_count > 0 ? h->sm_count : 148;
+    const bool narrow = (ncols + 255) / 256 < (int64_t)6 * sms;
+    const unsigned grid = narrow ? (unsigned)((ncols + 127) / 128) : (unsigned)((ncols + 255) / 256);
 #define GPX_APPEND_LAUNCH(F, S)                                                                                      \
     do {                                                                                                             \
         if (smem > 48 * 1024) {                                                                                      \
-            const int rc_ = gpx_ensure_smem(h, (const void*)append_row_kernel<F, S>, 200 * 1024, "append_row");      \
+            int rc_ = gpx_ensure_smem(h, (const void*)append_row_kernel<F, S, 128>, 200 * 1024, "append_row");       \
+            if (!rc_) rc_ = gpx_ensure_smem(h, (const void*)append_row_kernel<F, S, 64>, 200 * 1024, "append_row");  \
             if (rc_) return rc_;                                                                                     \
         }                                                                                                            \
-        append_row_kernel<F, S><<<grid, 128, smem, st>>>(h->kp, rec, src_row, Y, ncols, ldy, W, ldw, (int)n, var);    \
+        if (narrow)                                                                                                  \
+            append_row_kernel<F, S, 64><<<grid, 64, smem, st>>>(h->kp, rec, src_row, Y, ncols, ldy, W, ldw, (int)n, var); \
+        else                                                                                                         \
+            append_row_kernel<F, S, 128><<<grid, 128, smem, st>>>(h->kp, rec, src_row, Y, ncols, ldy, W, ldw, (int)n, var); \
     } while (0)
     if (row_source == GPX_ROW_KERNEL) {
         GPX_DISPATCH_FAMILY(h->kp.family, GPX_APPEND_LAUNCH(FAM, GPX_ROW_KERNEL));
@@ -874,7 +882,7 @@ extern "C" int gpx_add_at_rows(gpx_handle h, double* A, int64_t ld, const int64_
 // in the same pass: 16 bytes of HBM traffic per (m,c) pair and step, independent of the design size n.
 // Block = 512 columns (16-byte accesses) x one row segment; per-segment partial sums are added in a fixed order.
 // ---------------------------------------------------------------------------------------------
-#define COV_MAX_SEG 32
+#define COV_MAX_SEG 160
 
 __global__ void __launch_bounds__(256) cov_update_kernel(double* __restrict__ cov, int64_t ldc, int64_t M, int64_t C,
                                                           const double* __restrict__ a, const double* __restrict__ b,
@@ -931,8 +939,16 @@ __global__ void __launch_bounds__(256) cov_update_kernel(double* __restrict__ co
     if (c + 1 < C) dst[1] = r1;
 }
 
-extern "C" int gpx_cov_segments(int64_t M) {
+extern "C" int gpx_cov_segments(int64_t M, int64_t C) {
+    // row segments: ~2048 rows each for wide candidate sets; more (down to 64 rows) when few 512-column blocks would
+    // otherwise leave most of the 148 SMs idle (cfg-1: 1 000 candidates = 2 column blocks)
     int64_t s = (M + 2047) / 2048;
+    const int64_t colblocks = (C + 511) / 512;
+    if (colblocks > 0 && s * colblocks < 2 * 148) {
+        s = (2 * 148 + colblocks - 1) / colblocks;
+        const int64_t cap = (M + 63) / 64;
+        if (s > cap) s = cap;
+    }
     if (s < 1) s = 1;
     if (s > COV_MAX_SEG) s = COV_MAX_SEG;
     return (int)s;
@@ -946,7 +962,7 @@ extern "C" int gpx_cov_update(gpx_handle h, double* cov, int64_t ldc, int64_t M,
                 "cov must be 16-byte aligned with an even leading dimension");
     GPX_REQUIRE(b == nullptr || gpx_aligned16(b), GPX_EALIGN, "b must be 16-byte aligned");
     GPX_REQUIRE(ldp >= C, GPX_EINVAL, "partial rows too short");
-    const int seg = gpx_cov_segments(M);
+    const int seg = gpx_cov_segments(M, C);
     const int64_t rows = (M + seg - 1) / seg;
     dim3 grid((unsigned)((C + 511) / 512), (unsigned)seg);
     cov_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cov, ldc, M, C, a, b, rows, partial, ldp);

@@ -1064,8 +1064,11 @@ int gpx_launch_core_ivar(gpx_handle h, int prologue, const double* Wm, int64_t l
         const int64_t groups = (jt + gw - 1) / gw;
         a.upper_only = (int)gw;
         a.ldo_splits = splits;
-        // every group gets gw*splits CTA slots; the short last group leaves some idle (they exit at once)
-        dim3 grid((unsigned)(groups * gw * splits), 1u);
+        // a group of g tiles owns g*splits consecutive CTAs; only the last group can be short, and the kernel's index
+        // decode needs nothing beyond it, so the grid is exactly jt*splits CTAs (round 1 padded the last group to
+        // gw*splits slots: 2 520 CTAs that exited at once per cfg-1 step, ~25 us of launch work)
+        (void)groups;
+        dim3 grid((unsigned)(jt * splits), 1u);
         if (prologue == PRO_DIFF) {
             GPX_DISPATCH_FAMILY(h->kp.family, rc = (launch_ivar_ws<FAM, PRO_DIFF>(h, a, grid, st)));
         } else {

@@ -228,15 +228,15 @@ struct AppendSide {
     double* var;
 };
 
-template <int FAM>
-__global__ void __launch_bounds__(128) append_row2_kernel(const __grid_constant__ KParams kp, const double* __restrict__ rec,
-                                                           AppendSide s0, AppendSide s1, unsigned blocks0, int n) {
+template <int FAM, int NT>
+__global__ void __launch_bounds__(NT) append_row2_kernel(const __grid_constant__ KParams kp, const double* __restrict__ rec,
+                                                          AppendSide s0, AppendSide s1, unsigned blocks0, int n) {
     extern __shared__ double sl[];
-    for (int i = threadIdx.x; i < n; i += 128) sl[i] = rec[GPX_PIVOT_HDR + i];
+    for (int i = threadIdx.x; i < n; i += NT) sl[i] = rec[GPX_PIVOT_HDR + i];
     __syncthreads();
     const bool first = blockIdx.x < blocks0;
     const AppendSide& s = first ? s0 : s1;
-    const int64_t j = ((int64_t)(first ? blockIdx.x : blockIdx.x - blocks0) * 128 + threadIdx.x) * 2;
+    const int64_t j = ((int64_t)(first ? blockIdx.x : blockIdx.x - blocks0) * NT + threadIdx.x) * 2;
     if (j >= s.ncols) return;
     const double* wp = s.W + j;
     const int64_t ldw = s.ldw;
@@ -315,11 +315,19 @@ template <int FAM>
 int launch_append2_fam(gpx_handle h, const double* rec, const AppendSide& s0, const AppendSide& s1, int64_t n, cudaStream_t st) {
     const size_t smem = (size_t)n * sizeof(double);
     if (smem > 48 * 1024) {
-        int rc = gpx_ensure_smem(h, (const void*)append_row2_kernel<FAM>, 200 * 1024, "append_row2");
+        int rc = gpx_ensure_smem(h, (const void*)append_row2_kernel<FAM, 128>, 200 * 1024, "append_row2");
+        if (!rc) rc = gpx_ensure_smem(h, (const void*)append_row2_kernel<FAM, 64>, 200 * 1024, "append_row2");
         if (rc) return rc;
     }
-    const unsigned b0 = (unsigned)((s0.ncols + 255) / 256), b1 = (unsigned)((s1.ncols + 255) / 256);
-    append_row2_kernel<FAM><<<b0 + b1, 128, smem, st>>>(h->kp, rec, s0, s1, b0, (int)n);
+    // narrow problems (fewer than ~6 blocks of 256 columns per SM) run 64-thread blocks, as gpx_append_row does
+    const int sms = h->sm_count > 0 ? h->sm_count : 148;
+    if ((s0.ncols + s1.ncols + 255) / 256 < (int64_t)6 * sms) {
+        const unsigned b0 = (unsigned)((s0.ncols + 127) / 128), b1 = (unsigned)((s1.ncols + 127) / 128);
+        append_row2_kernel<FAM, 64><<<b0 + b1, 64, smem, st>>>(h->kp, rec, s0, s1, b0, (int)n);
+    } else {
+        const unsigned b0 = (unsigned)((s0.ncols + 255) / 256), b1 = (unsigned)((s1.ncols + 255) / 256);
+        append_row2_kernel<FAM, 128><<<b0 + b1, 128, smem, st>>>(h->kp, rec, s0, s1, b0, (int)n);
+    }
     return gpx_check_launch("greedy append");
 }
 

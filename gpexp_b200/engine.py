@@ -530,13 +530,14 @@ class GreedyIVAREngine(_Pivoting):
         self.U = dev.zeros(ncap, roundup(ncap))
         check(lib.gpx_prior_diag(dev.h, ptr(cand.X), cand.n, cand.ld, ptr(self.varC), dev.stream), "gpx_prior_diag")
         check(lib.gpx_prior_diag(dev.h, ptr(mc.X), mc.n, mc.ld, ptr(self.varM), dev.stream), "gpx_prior_diag")
-        ws = int(lib.gpx_score_ivar_workspace(dev.h, mc.n, cand.n))
+        self.nseg = int(lib.gpx_cov_segments(mc.n, cand.n))
+        self.ldp = (cand.n + 1) & ~1
+        # partial column sums: M-splits of the contraction, or row segments of the resident update
+        ws = max(int(lib.gpx_score_ivar_workspace(dev.h, mc.n, cand.n)), self.nseg * self.ldp)
         self.workspace = dev.zeros(max(ws, 1))
         self.scores = dev.zeros(cand.ld)
         self.score_trace = None
         self.cov = None
-        self.nseg = int(lib.gpx_cov_segments(mc.n))
-        self.ldp = (cand.n + 1) & ~1
         self.zero_scale = float(zero_scale)
         if self.resident:
             self.cov = dev.empty(mc.n, cand.ld)

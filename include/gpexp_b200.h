@@ -218,8 +218,8 @@ int gpx_score_ivar(gpx_handle h, int prologue, const double* Wm, int64_t ldm, co
 /* ---- Resident posterior covariance: the HBM-bound alternative for greedy IVAR loops -----------
  * cov (M x ldcov, row m = integration point, 8*M*C bytes resident) holds cov_D(m,c); each greedy step is ONE pass
  *     cov -= a b^T ,  partial[seg][c] = sum_{m in seg} cov[m,c]^2          (16 B of HBM traffic per pair, any n)
- * a = new row of W_M (M), b = new row of W_C (C); a = b = NULL only reduces.  partial: gpx_cov_segments(M) x ldp. */
-int gpx_cov_segments(int64_t M);
+ * a = new row of W_M (M), b = new row of W_C (C); a = b = NULL only reduces.  partial: gpx_cov_segments(M, C) x ldp. */
+int gpx_cov_segments(int64_t M, int64_t C);
 int gpx_cov_update(gpx_handle h, double* cov, int64_t ldcov, int64_t M, int64_t C, const double* a, const double* b,
                    double* partial, int64_t ldp, void* stream);
 /* cov = K(mc, cand) - Wm^T Wc for a given design (DMMA contraction, Gram in the prologue); n = 0 gives K itself. */
@@ -305,7 +305,7 @@ typedef struct gpx_ivar_state {
     int64_t ncap;          /* rows allocated in Wm / Wc */
     int64_t index_offset;  /* global index of local candidate 0 */
     int prologue;          /* GPX_PRO_EXPANDED | GPX_PRO_DIFF */
-    int nseg;              /* resident mode: gpx_cov_segments(M) */
+    int nseg;              /* resident mode: gpx_cov_segments(M, C) */
     double noise, zero_tol;
     double* workspace;     /* gpx_score_ivar_workspace doubles */
     double* scores;        /* ldc */

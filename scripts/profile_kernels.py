@@ -84,6 +84,9 @@ for name, kern, d in [("se_2d", kernels.KernelSquaredExponential([0.06, 0.09], 1
     rec[2] = 1.0
     t = ev_ms(lambda: check(lib.gpx_append_row(dev.h, 0, ptr(rec), None, ptr(X.X), C, X.ld, ptr(W), X.ld, n - 1, ptr(var), dev.stream)), 10)
     out[f"append_{name}_n{n - 1}_gbs"] = 8.0 * (n + 1) * C / t / 1e6
+    t = ev_ms(lambda: check(lib.gpx_append_row(dev.h, 0, ptr(rec), None, ptr(X.X), C, X.ld, ptr(W), X.ld, 255, ptr(var), dev.stream)), 20)
+    out[f"append_{name}_n255_gbs"] = 8.0 * 257 * C / t / 1e6
+    out[f"append_{name}_n255_us"] = t * 1e3
     del W, f
 print(json.dumps(out, indent=1))
 if not once:
