@@ -473,22 +473,16 @@ extern "C" int gpx_append_row(gpx_handle h, int row_source, const double* rec, c
     const size_t smem = (size_t)n * sizeof(double);
     GPX_REQUIRE(smem <= 200 * 1024, GPX_ESIZE, "design size exceeds the shared-memory column buffer (25600)");
     cudaStream_t st = (cudaStream_t)stream;
-    // 256 columns per 128-thread block; with fewer than ~6 such blocks per SM (C = 1e5: 2.6) the SMs are unevenly loaded
-    // and too few loads are in flight during the ramp, so narrow problems run 64-thread blocks of 128 columns
-    const int sms = h->sm_count > 0 ? h->sm_count : 148;
-    const bool narrow = (ncols + 255) / 256 < (int64_t)6 * sms;
-    const unsigned grid = narrow ? (unsigned)((ncols + 127) / 128) : (unsigned)((ncols + 255) / 256);
+    // 256 columns per 128-thread block.  (Measured in round 2: 64-thread blocks for narrow problems change nothing --
+    // 48.1 vs 46 us at n = 255, C = 1e5: the 31 us of streaming sit between ~15 us of launch, ramp and tail.)
+    const unsigned grid = (unsigned)((ncols + 255) / 256);
 #define GPX_APPEND_LAUNCH(F, S)                                                                                      \
     do {                                                                                                             \
         if (smem > 48 * 1024) {                                                                                      \
-            int rc_ = gpx_ensure_smem(h, (const void*)append_row_kernel<F, S, 128>, 200 * 1024, "append_row");       \
-            if (!rc_) rc_ = gpx_ensure_smem(h, (const void*)append_row_kernel<F, S, 64>, 200 * 1024, "append_row");  \
+            const int rc_ = gpx_ensure_smem(h, (const void*)append_row_kernel<F, S, 128>, 200 * 1024, "append_row"); \
             if (rc_) return rc_;                                                                                     \
         }                                                                                                            \
-        if (narrow)                                                                                                  \
-            append_row_kernel<F, S, 64><<<grid, 64, smem, st>>>(h->kp, rec, src_row, Y, ncols, ldy, W, ldw, (int)n, var); \
-        else                                                                                                         \
-            append_row_kernel<F, S, 128><<<grid, 128, smem, st>>>(h->kp, rec, src_row, Y, ncols, ldy, W, ldw, (int)n, var); \
+        append_row_kernel<F, S, 128><<<grid, 128, smem, st>>>(h->kp, rec, src_row, Y, ncols, ldy, W, ldw, (int)n, var); \
     } while (0)
     if (row_source == GPX_ROW_KERNEL) {
         GPX_DISPATCH_FAMILY(h->kp.family, GPX_APPEND_LAUNCH(FAM, GPX_ROW_KERNEL));

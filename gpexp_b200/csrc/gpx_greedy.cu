@@ -316,18 +316,10 @@ int launch_append2_fam(gpx_handle h, const double* rec, const AppendSide& s0, co
     const size_t smem = (size_t)n * sizeof(double);
     if (smem > 48 * 1024) {
         int rc = gpx_ensure_smem(h, (const void*)append_row2_kernel<FAM, 128>, 200 * 1024, "append_row2");
-        if (!rc) rc = gpx_ensure_smem(h, (const void*)append_row2_kernel<FAM, 64>, 200 * 1024, "append_row2");
         if (rc) return rc;
     }
-    // narrow problems (fewer than ~6 blocks of 256 columns per SM) run 64-thread blocks, as gpx_append_row does
-    const int sms = h->sm_count > 0 ? h->sm_count : 148;
-    if ((s0.ncols + s1.ncols + 255) / 256 < (int64_t)6 * sms) {
-        const unsigned b0 = (unsigned)((s0.ncols + 127) / 128), b1 = (unsigned)((s1.ncols + 127) / 128);
-        append_row2_kernel<FAM, 64><<<b0 + b1, 64, smem, st>>>(h->kp, rec, s0, s1, b0, (int)n);
-    } else {
-        const unsigned b0 = (unsigned)((s0.ncols + 255) / 256), b1 = (unsigned)((s1.ncols + 255) / 256);
-        append_row2_kernel<FAM, 128><<<b0 + b1, 128, smem, st>>>(h->kp, rec, s0, s1, b0, (int)n);
-    }
+    const unsigned b0 = (unsigned)((s0.ncols + 255) / 256), b1 = (unsigned)((s1.ncols + 255) / 256);
+    append_row2_kernel<FAM, 128><<<b0 + b1, 128, smem, st>>>(h->kp, rec, s0, s1, b0, (int)n);
     return gpx_check_launch("greedy append");
 }
 
