@@ -539,14 +539,22 @@ def run_ours(args):
     parity = cfg5 = None
     del eng
     torch.cuda.empty_cache()
+
+    def guarded(fn, *a):
+        """The side blocks must not cost the headline line: a failure is reported in place of the block's result."""
+        try:
+            return fn(*a)
+        except Exception as e:  # noqa: BLE001
+            torch.cuda.empty_cache()
+            return {"error": f"{type(e).__name__}: {e}"[:400]} if rank == 0 else None
     if world > 1 and not args.no_parity:
-        parity = parity_block(ed, gpmod, kernels, Space, ShardedMIEngine, Device, shard, dist, torch, rank, world)
+        parity = guarded(parity_block, ed, gpmod, kernels, Space, ShardedMIEngine, Device, shard, dist, torch, rank, world)
     if world >= 8 and not args.no_cfg5:
-        cfg5 = cfg5_block(ed, gpmod, kernels, Space, shard, dist, torch, rank, world, local, dgemm_tflops)
+        cfg5 = guarded(cfg5_block, ed, gpmod, kernels, Space, shard, dist, torch, rank, world, local, dgemm_tflops)
     cfg3 = cfg4 = None
     if not args.no_configs:
-        cfg3 = cfg3_block(ed, kernels, shard, dist, torch, rank, world)
-        cfg4 = cfg4_block(ed, gpmod, kernels, Space, shard, dist, torch, rank, world)
+        cfg3 = guarded(cfg3_block, ed, kernels, shard, dist, torch, rank, world)
+        cfg4 = guarded(cfg4_block, ed, gpmod, kernels, Space, shard, dist, torch, rank, world)
 
     if rank != 0:
         if world > 1:

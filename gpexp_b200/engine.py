@@ -24,7 +24,7 @@ import torch
 
 from . import _lib
 from ._lib import GpxError, check, lib
-from .device import Device, PointSet, F64, prologue_operands, ptr, roundup
+from .device import Device, PointSet, prologue_operands, ptr, roundup
 
 HDR = _lib.GPX_PIVOT_HDR
 ZERO_VAR_TOL = 1e-13

@@ -19,7 +19,6 @@ import itertools
 
 import numpy as np
 
-from . import _lib
 from ._lib import check, lib
 from .device import ptr
 from .engine import (DesignFactor, GreedyIVAREngine, GreedyVarEngine, Shard, ShardedMIEngine, prior_scale)
