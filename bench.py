@@ -692,7 +692,8 @@ def run_ours(args):
             torch.cuda.synchronize()
             cfg1["resident_ms" if resident else "contraction_ms"] = (time.perf_counter() - t0) * 1e3
             cfg1["picks"] = [int(i) for i in e1_.indices()[:6]]
-        cfg1["note"] = "whole 20-point design of configs[0] (1 000 candidates x 10 000 MC points), wall clock of one run() call"
+        cfg1["note"] = ("whole 20-point design of configs[0] (1 000 candidates x 10 000 MC points), wall clock of one run() call: "
+                        "contraction = 20 x 5 launches from the C-side loop, resident = ONE cooperative kernel (gpx_ivar_greedy_small)")
         # resident-covariance mode of the same greedy loop (HBM-bound, 16*M*C bytes per step)
         kern._bind(dev)
         torch.cuda.empty_cache()

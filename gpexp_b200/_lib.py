@@ -113,6 +113,7 @@ SIGNATURES = {
     "gpx_comm_bcast": [_p, _p, _i64, _int, _p],
     "gpx_comm_allreduce_sum": [_p, _p, _i64, _p],
     "gpx_ivar_greedy_run": [_p, C.POINTER(IvarState), _i64, _i64, _p],
+    "gpx_ivar_greedy_small": [_p, C.POINTER(IvarState), _i64, _i64, _p],
     "gpx_var_greedy_run": [_p, C.POINTER(VarState), _i64, _i64, _p],
     "gpx_state_bytes": [_int],
     "gpx_se_dgram": [_p, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p],

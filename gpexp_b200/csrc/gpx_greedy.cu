@@ -13,6 +13,7 @@
 //
 // NCCL is resolved at run time (dlopen of the libnccl.so.2 the process already has, e.g. the one PyTorch loaded), so the
 // library has no link-time dependency on it; a caller that never calls gpx_comm_init never touches it.
+#include <cooperative_groups.h>
 #include <dlfcn.h>
 #include <math.h>
 #include <string.h>
@@ -339,6 +340,224 @@ int exchange(gpx_handle h, const double* rec, double* rec_all, double* rec_win, 
 }
 
 }  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// Small problems (configs[0]: 1 000 candidates x 10 000 MC points): the whole greedy IVAR loop as ONE cooperative kernel.
+// The multi-launch loop above is bound by launch issue (~12 us per launch, 5 per step); here a step is three grid-wide
+// phases separated by grid.sync():
+//   A  scores from the resident column sums (same finalisation as ivar_finalize_argmin_kernel) + per-block arg-min
+//   B  global arg-min (every block, identical), pivot record, new rows of W_C and W_M, running variances, history
+//   C  cov -= w_M[n] w_C[n]^T with the next step's column sums of squares (same layout as gpx_cov_update)
+// State conventions at entry and exit are those of the resident engine (cov current, partial sums valid), so the two
+// paths can be mixed.  The winner's pivot var_D(p) + noise travels with the block results: it must be read before any
+// block starts updating the variances in phase B.
+// ---------------------------------------------------------------------------------------------
+namespace {
+namespace cg = cooperative_groups;
+constexpr int SMALL_NCAP = 1024;   // design points whose pivot column fits the shared-memory buffer
+
+__device__ __forceinline__ double small_block_sum(double v, double* sm) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w];
+    return t;  // every thread holds the same total (fixed order)
+}
+
+__device__ __forceinline__ void small_block_argmin(double& v, int64_t& i, double& aux, double* sv, int64_t* si, double* sa) {
+    // (value, index) minimum with np.argmin tie-break; aux travels with the winner
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+        const int64_t oi = __shfl_xor_sync(0xffffffffu, i, off);
+        const double oa = __shfl_xor_sync(0xffffffffu, aux, off);
+        if (gpx_better(ov, oi, v, i, true)) {
+            v = ov;
+            i = oi;
+            aux = oa;
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) {
+        sv[warp] = v;
+        si[warp] = i;
+        sa[warp] = aux;
+    }
+    __syncthreads();
+    v = sv[0];
+    i = si[0];
+    aux = sa[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w)
+        if (gpx_better(sv[w], si[w], v, i, true)) {
+            v = sv[w];
+            i = si[w];
+            aux = sa[w];
+        }
+}
+
+template <int FAM>
+__global__ void __launch_bounds__(256, 2) ivar_small_greedy_kernel(const __grid_constant__ KParams kp, const gpx_ivar_state s,
+                                                                 int n_begin, int n_end, double* __restrict__ blk_val,
+                                                                 int64_t* __restrict__ blk_idx, double* __restrict__ blk_piv) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sm[8], sa[8], s_col[SMALL_NCAP], s_xp[GPX_MAX_DIM];
+    __shared__ int64_t si[8];
+    const int tid = threadIdx.x;
+    const int64_t nb = gridDim.x, b = blockIdx.x;
+    const int64_t M = s.M, C = s.C;
+    const int64_t colchunks = (C + 255) / 256;
+    const int64_t rows_per_seg = (M + s.nseg - 1) / s.nseg;
+    for (int n = n_begin; n < n_end; ++n) {
+        // ---- phase A: base = mean of var_M (every block, same order), scores of my candidates, block arg-min -----------
+        double part = 0.0;
+        for (int64_t m = tid; m < M; m += 256) part += s.varM[m];
+        const double base = small_block_sum(part, sm) / (double)M;     // (1/nMC) sum varMC   experimentalDesign.py:109
+        double bv = 0.0, bp = 1.0;
+        int64_t bi = -1;
+        for (int64_t c = b * 256 + tid; c < C; c += nb * 256) {
+            double r = 0.0;
+            for (int g = 0; g < s.nseg; ++g) r += s.workspace[(int64_t)g * s.ldp + c];
+            const double den = s.varC[c] + s.noise;
+            const double red = (den <= s.zero_tol) ? 0.0 : (r / den) / (double)M;
+            const double sc = fabs(base - red);                         // np.abs(cost)        experimentalDesign.py:117
+            s.scores[c] = sc;
+            if (gpx_better(sc, c, bv, bi, true)) {
+                bv = sc;
+                bi = c;
+                bp = den;
+            }
+        }
+        small_block_argmin(bv, bi, bp, sm, si, sa);
+        if (tid == 0) {
+            blk_val[b] = bv;
+            blk_idx[b] = bi;
+            blk_piv[b] = bp;
+        }
+        grid.sync();
+        // ---- phase B: the winner (identical in every block), its record, the new rows ---------------------------------
+        bv = 0.0;
+        bp = 1.0;
+        bi = -1;
+        for (int64_t q = tid; q < nb; q += 256) {
+            const double ov = __ldcg(blk_val + q);
+            const int64_t oi = __ldcg(blk_idx + q);
+            if (gpx_better(ov, oi, bv, bi, true)) {
+                bv = ov;
+                bi = oi;
+                bp = __ldcg(blk_piv + q);
+            }
+        }
+        small_block_argmin(bv, bi, bp, sm, si, sa);
+        const int64_t p = bi;
+        const double piv = bp;
+        for (int i = tid; i < n; i += 256) s_col[i] = s.Wc[(int64_t)i * s.ldc + p];
+        if (tid < GPX_MAX_DIM) s_xp[tid] = tid < kp.d ? s.Xc[tid * s.ldc + p] : 0.0;
+        __syncthreads();
+        if (b == 0) {
+            for (int i = tid; i < n; i += 256)
+                if (s.U) s.U[(int64_t)i * s.ldu + n] = s_col[i];
+            if (tid == 0) {
+                if (s.U) s.U[(int64_t)n * s.ldu + n] = sqrt(piv);
+                s.picks[n] = p + s.index_offset;
+                if (s.pick_scores) s.pick_scores[n] = bv;
+                if (s.pick_pivots) s.pick_pivots[n] = piv;
+                s.best[0] = bv;
+                s.idx[0] = p;
+            }
+        }
+        const double lnn = piv > 0.0 ? sqrt(piv) : INFINITY;            // non-positive pivot -> zero row (append_row_kernel)
+        for (int64_t j = b * 256 + tid; j < C + M; j += nb * 256) {
+            const bool cside = j < C;
+            const int64_t col = cside ? j : j - C;
+            const int64_t ld = cside ? s.ldc : s.ldm;
+            double* W = cside ? s.Wc : s.Wm;
+            const double* X = cside ? s.Xc : s.Xm;
+            double* var = cside ? s.varC : s.varM;
+            double a = 0.0;
+            for (int i = 0; i < n; ++i) a = fma(s_col[i], W[(int64_t)i * ld + col], a);
+            double k = 0.0;
+#pragma unroll
+            for (int q = 0; q < GPX_MAX_DIM; ++q)
+                if (q < kp.d) kacc_dim<FAM>(k, kp, q, s_xp[q], X[q * ld + col]);
+            const double w = (kfinish<FAM>(k, kp) - a) / lnn;
+            W[(int64_t)n * ld + col] = w;
+            var[col] -= w * w;
+        }
+        grid.sync();
+        // ---- phase C: cov -= w_M[n] w_C[n]^T and the column sums of squares of the next step ----------------------------
+        const double* am = s.Wm + (int64_t)n * s.ldm;
+        const double* bc = s.Wc + (int64_t)n * s.ldc;
+        for (int64_t item = b; item < (int64_t)s.nseg * colchunks; item += nb) {
+            const int64_t seg = item / colchunks, c = (item % colchunks) * 256 + tid;
+            if (c >= C) continue;
+            const int64_t m0 = seg * rows_per_seg;
+            const int64_t m1 = m0 + rows_per_seg < M ? m0 + rows_per_seg : M;
+            const double bcol = bc[c];
+            double r = 0.0;
+            double* cp = s.cov + m0 * s.ldcov + c;
+            for (int64_t m = m0; m < m1; ++m, cp += s.ldcov) {
+                const double v = fma(-am[m], bcol, *cp);
+                *cp = v;
+                r = fma(v, v, r);
+            }
+            s.workspace[seg * s.ldp + c] = r;
+        }
+        grid.sync();
+    }
+}
+
+}  // namespace
+
+// Whole greedy IVAR loop in one cooperative launch, for a RESIDENT engine state on one GPU (s->cov != NULL, no
+// communicator): steps n_begin .. n_end-1.  Meant for small problems (the covariance M x C should fit the L2 cache);
+// correct for any size.  n_end <= 1024.
+extern "C" int gpx_ivar_greedy_small(gpx_handle h, const gpx_ivar_state* s, int64_t n_begin, int64_t n_end, void* stream) {
+    GPX_NEED_KERNEL(h);
+    GPX_REQUIRE(s != nullptr, GPX_EINVAL, "state is NULL");
+    GPX_REQUIRE(n_begin >= 0 && n_end >= n_begin && n_end <= s->ncap && n_end <= SMALL_NCAP, GPX_ESIZE,
+                "step range outside the state's capacity or beyond 1024 design points");
+    GPX_REQUIRE(s->cov && s->Xm && s->Wm && s->varM && s->Xc && s->Wc && s->varC && s->workspace && s->scores && s->best &&
+                    s->idx && s->picks && s->M >= 1 && s->C >= 1 && s->nseg >= 1 && s->ldp >= s->C && s->ldcov >= s->C,
+                GPX_EINVAL, "the one-kernel loop needs a complete resident state");
+    GPX_REQUIRE(h->nccl_comm == nullptr || h->comm_size <= 1 || s->rec_all == nullptr, GPX_EINVAL,
+                "the one-kernel loop is single-GPU");
+    if (n_end == n_begin) return GPX_OK;
+    int per_sm = 0;
+    cudaError_t e;
+#define GPX_SMALL_LAUNCH(F)                                                                                              \
+    do {                                                                                                                 \
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ivar_small_greedy_kernel<F>, 256, 0);                 \
+        if (e == cudaSuccess) {                                                                                          \
+            if (per_sm > 2) per_sm = 2;                                                                                  \
+            int blocks = per_sm * (h->sm_count > 0 ? h->sm_count : 148);                                                 \
+            if (blocks > 1024) blocks = 1024;                                                                            \
+            KParams kp = h->kp;                                                                                          \
+            gpx_ivar_state st = *s;                                                                                      \
+            int nb0 = (int)n_begin, ne0 = (int)n_end;                                                                    \
+            double* bv = h->red_val;                                                                                     \
+            int64_t* bi = h->red_idx;                                                                                    \
+            double* bp = h->red_val + 1024;                                                                              \
+            void* args[] = {&kp, &st, &nb0, &ne0, &bv, &bi, &bp};                                                        \
+            e = blocks > 0 ? cudaLaunchCooperativeKernel((const void*)ivar_small_greedy_kernel<F>, dim3(blocks), dim3(256), \
+                                                         args, 0, (cudaStream_t)stream)                                  \
+                           : cudaErrorLaunchOutOfResources;                                                              \
+        }                                                                                                                \
+    } while (0)
+    GPX_DISPATCH_FAMILY(h->kp.family, GPX_SMALL_LAUNCH(FAM));
+#undef GPX_SMALL_LAUNCH
+    if (e != cudaSuccess) {
+        gpx_set_error("gpx_ivar_greedy_small: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return gpx_check_launch("gpx_ivar_greedy_small");
+}
 
 // sizeof of the state structs as this library was compiled: lets a binding verify its own layout
 extern "C" int64_t gpx_state_bytes(int which) {

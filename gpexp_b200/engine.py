@@ -512,6 +512,10 @@ class GreedyIVAREngine(_Pivoting):
     """Discrete greedy IVAR: every step scores all candidates with the FP64 DMMA
     contraction (K5), takes the arg-min, and appends one row to W_C and W_M."""
 
+    # resident problems up to this many (integration point, candidate) pairs run their whole loop as ONE cooperative
+    # kernel (gpx_ivar_greedy_small): 256 MB of covariance, roughly what stays close to the 126 MB L2
+    ONE_KERNEL_PAIRS = 32_000_000
+
     def __init__(self, dev: Device, cand: PointSet, mc: PointSet, n_max: int, noise: float, zero_scale: float,
                  shard=None, index_offset: int = 0, resident: bool = False):
         """resident=True keeps the posterior covariance cov_D(m, c) (8*M*C bytes) in HBM and replaces the per-step
@@ -672,11 +676,15 @@ class GreedyIVAREngine(_Pivoting):
                 self.step()
             return self.indices()
         st = self._state()
+        # small resident problems on one GPU: the whole loop as one cooperative kernel (no per-launch issue cost)
+        one_kernel = (self.resident and (self.shard is None or self.shard.world == 1) and n_points <= 1024 and
+                      self.mc.n * self.cand.n <= self.ONE_KERNEL_PAIRS)
+        run = lib.gpx_ivar_greedy_small if one_kernel else lib.gpx_ivar_greedy_run
         while self.n < n_points:
             if progress is not None:
                 progress(self.n)
             stop = min(n_points, (self.n // chunk + 1) * chunk) if progress is not None else n_points
-            check(lib.gpx_ivar_greedy_run(self.dev.h, C.byref(st), self.n, stop, self.dev.stream), "gpx_ivar_greedy_run")
+            check(run(self.dev.h, C.byref(st), self.n, stop, self.dev.stream), "gpx_ivar_greedy_run")
             self.n = stop
         return self.indices()
 
