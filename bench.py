@@ -693,7 +693,9 @@ def run_ours(args):
             cfg1["resident_ms" if resident else "contraction_ms"] = (time.perf_counter() - t0) * 1e3
             cfg1["picks"] = [int(i) for i in e1_.indices()[:6]]
         cfg1["note"] = ("whole 20-point design of configs[0] (1 000 candidates x 10 000 MC points), wall clock of one run() call: "
-                        "contraction = 20 x 5 launches from the C-side loop, resident = ONE cooperative kernel (gpx_ivar_greedy_small)")
+                        "contraction = 20 x 5 launches from the C-side loop, resident = " +
+                        ("ONE cooperative kernel (gpx_ivar_greedy_small)" if type(e1_).ONE_KERNEL_PAIRS >= 10_000_000
+                         else "20 x 4 launches from the C-side loop"))
         # resident-covariance mode of the same greedy loop (HBM-bound, 16*M*C bytes per step)
         kern._bind(dev)
         torch.cuda.empty_cache()

@@ -17,6 +17,7 @@ to the lowest global index) -- so every rank appends bit-identical rows.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import warnings
 
 import numpy as np
@@ -513,8 +514,10 @@ class GreedyIVAREngine(_Pivoting):
     contraction (K5), takes the arg-min, and appends one row to W_C and W_M."""
 
     # resident problems up to this many (integration point, candidate) pairs run their whole loop as ONE cooperative
-    # kernel (gpx_ivar_greedy_small): 256 MB of covariance, roughly what stays close to the 126 MB L2
-    ONE_KERNEL_PAIRS = 32_000_000
+    # kernel (gpx_ivar_greedy_small): 256 MB of covariance, roughly what stays close to the 126 MB L2.
+    # GPX_ONE_KERNEL_PAIRS overrides (0 = always the multi-launch loop).
+    ONE_KERNEL_DEFAULT = 0
+    ONE_KERNEL_PAIRS = int(os.environ.get("GPX_ONE_KERNEL_PAIRS", ONE_KERNEL_DEFAULT))
 
     def __init__(self, dev: Device, cand: PointSet, mc: PointSet, n_max: int, noise: float, zero_scale: float,
                  shard=None, index_offset: int = 0, resident: bool = False):

@@ -16,14 +16,15 @@ rng = np.random.default_rng(1)
 cand, mc = rng.uniform(-1, 1, (1000, 1)), rng.uniform(-1, 1, (10000, 1))
 k = kernels.KernelSquaredExponential([0.05], 1.0, 1)
 cf = ed.costFunctionGP_IVAR(gp.GP(k, 1e-6), 1, Space(1, None, None), mcPoints=mc)
-for resident in (False, True):
+for resident, one_kernel in ((False, False), (True, False), (True, True)):
     for rep in range(2):
         eng = ed.beginGreedyIVARExperimentalDesign(cf, cand, 20, resident=resident)
+        eng.ONE_KERNEL_PAIRS = 32_000_000 if one_kernel else 0
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         eng.run(20)
         t1 = time.perf_counter()
         torch.cuda.synchronize()
         t2 = time.perf_counter()
-        print("resident" if resident else "contraction", "rep", rep, "issue %.3f ms  total %.3f ms" % ((t1 - t0) * 1e3, (t2 - t0) * 1e3),
+        print(("one-kernel" if one_kernel else "resident") if resident else "contraction", "rep", rep, "issue %.3f ms  total %.3f ms" % ((t1 - t0) * 1e3, (t2 - t0) * 1e3),
               [int(i) for i in eng.indices()[:4]], flush=True)
