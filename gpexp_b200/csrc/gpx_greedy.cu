@@ -355,6 +355,7 @@ int exchange(gpx_handle h, const double* rec, double* rec_all, double* rec_win, 
 namespace {
 namespace cg = cooperative_groups;
 constexpr int SMALL_NCAP = 1024;   // design points whose pivot column fits the shared-memory buffer
+constexpr int SMALL_SEG_PER_WARP = 20;  // COV_MAX_SEG (160) row segments over 8 warps
 
 __device__ __forceinline__ double small_block_sum(double v, double* sm) {
 #pragma unroll
@@ -405,40 +406,83 @@ __device__ __forceinline__ void small_block_argmin(double& v, int64_t& i, double
 template <int FAM>
 __global__ void __launch_bounds__(256, 2) ivar_small_greedy_kernel(const __grid_constant__ KParams kp, const gpx_ivar_state s,
                                                                  int n_begin, int n_end, double* __restrict__ blk_val,
-                                                                 int64_t* __restrict__ blk_idx, double* __restrict__ blk_piv) {
+                                                                 int64_t* __restrict__ blk_idx, double* __restrict__ blk_piv,
+                                                                 double* __restrict__ blk_base) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ double sm[8], sa[8], s_col[SMALL_NCAP], s_xp[GPX_MAX_DIM];
+    __shared__ double sm[8], sa[8], s_col[SMALL_NCAP], s_xp[GPX_MAX_DIM], s_part[8][32];
     __shared__ int64_t si[8];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t nb = gridDim.x, b = blockIdx.x;
     const int64_t M = s.M, C = s.C;
-    const int64_t colchunks = (C + 255) / 256;
+    const int64_t colblocks = (C + 511) / 512;
     const int64_t rows_per_seg = (M + s.nseg - 1) / s.nseg;
+    const int64_t cgroups = (C + 31) / 32;
+    // sum of var_M for the first step (every block, same order); later steps get it from the blocks' phase-B partials
+    double part = 0.0;
+    for (int64_t m = tid; m < M; m += 256) part += s.varM[m];
+    double base_sum = small_block_sum(part, sm);
     for (int n = n_begin; n < n_end; ++n) {
-        // ---- phase A: base = mean of var_M (every block, same order), scores of my candidates, block arg-min -----------
-        double part = 0.0;
-        for (int64_t m = tid; m < M; m += 256) part += s.varM[m];
-        const double base = small_block_sum(part, sm) / (double)M;     // (1/nMC) sum varMC   experimentalDesign.py:109
+        // ---- phase A: scores of my candidate groups (32 candidates x 8 warps over the row segments), block arg-min ------
+        const double base = base_sum / (double)M;                      // (1/nMC) sum varMC   experimentalDesign.py:109
         double bv = 0.0, bp = 1.0;
         int64_t bi = -1;
-        for (int64_t c = b * 256 + tid; c < C; c += nb * 256) {
-            double r = 0.0;
-            for (int g = 0; g < s.nseg; ++g) r += s.workspace[(int64_t)g * s.ldp + c];
-            const double den = s.varC[c] + s.noise;
-            const double red = (den <= s.zero_tol) ? 0.0 : (r / den) / (double)M;
-            const double sc = fabs(base - red);                         // np.abs(cost)        experimentalDesign.py:117
-            s.scores[c] = sc;
-            if (gpx_better(sc, c, bv, bi, true)) {
-                bv = sc;
-                bi = c;
-                bp = den;
+        for (int64_t grp = b; grp < cgroups; grp += nb) {
+            const int64_t c = grp * 32 + lane;
+            double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+            double den = 1.0;
+            if (c < C) {
+                // all of this warp's segment partials in one batch of loads (nseg <= 160 = 8 warps x 20)
+                const double* wp = s.workspace + c;
+                double v[SMALL_SEG_PER_WARP];
+#pragma unroll
+                for (int u = 0; u < SMALL_SEG_PER_WARP; ++u) {
+                    const int g = warp + 8 * u;
+                    v[u] = g < s.nseg ? wp[(int64_t)g * s.ldp] : 0.0;
+                }
+                if (warp == 0) den = s.varC[c] + s.noise;
+#pragma unroll
+                for (int u = 0; u < SMALL_SEG_PER_WARP; u += 4) {
+                    r0 += v[u];
+                    r1 += v[u + 1];
+                    r2 += v[u + 2];
+                    r3 += v[u + 3];
+                }
+                for (int g = warp + 8 * SMALL_SEG_PER_WARP; g < s.nseg; g += 8) r0 += wp[(int64_t)g * s.ldp];
+            }
+            __syncthreads();
+            s_part[warp][lane] = (r0 + r1) + (r2 + r3);
+            __syncthreads();
+            if (warp == 0 && c < C) {
+                double r = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) r += s_part[w][lane];
+                const double red = (den <= s.zero_tol) ? 0.0 : (r / den) / (double)M;
+                const double sc = fabs(base - red);                     // np.abs(cost)        experimentalDesign.py:117
+                s.scores[c] = sc;
+                if (gpx_better(sc, c, bv, bi, true)) {
+                    bv = sc;
+                    bi = c;
+                    bp = den;
+                }
             }
         }
-        small_block_argmin(bv, bi, bp, sm, si, sa);
-        if (tid == 0) {
-            blk_val[b] = bv;
-            blk_idx[b] = bi;
-            blk_piv[b] = bp;
+        if (warp == 0) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                const double oa = __shfl_xor_sync(0xffffffffu, bp, off);
+                if (gpx_better(ov, oi, bv, bi, true)) {
+                    bv = ov;
+                    bi = oi;
+                    bp = oa;
+                }
+            }
+            if (lane == 0) {
+                blk_val[b] = bv;
+                blk_idx[b] = bi;
+                blk_piv[b] = bp;
+            }
         }
         grid.sync();
         // ---- phase B: the winner (identical in every block), its record, the new rows ---------------------------------
@@ -473,6 +517,7 @@ __global__ void __launch_bounds__(256, 2) ivar_small_greedy_kernel(const __grid_
             }
         }
         const double lnn = piv > 0.0 ? sqrt(piv) : INFINITY;            // non-positive pivot -> zero row (append_row_kernel)
+        double vpart = 0.0;
         for (int64_t j = b * 256 + tid; j < C + M; j += nb * 256) {
             const bool cside = j < C;
             const int64_t col = cside ? j : j - C;
@@ -480,35 +525,95 @@ __global__ void __launch_bounds__(256, 2) ivar_small_greedy_kernel(const __grid_
             double* W = cside ? s.Wc : s.Wm;
             const double* X = cside ? s.Xc : s.Xm;
             double* var = cside ? s.varC : s.varM;
-            double a = 0.0;
-            for (int i = 0; i < n; ++i) a = fma(s_col[i], W[(int64_t)i * ld + col], a);
+            const double* wp = W + col;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            const double var_old = var[col];
+            int i = 0;
+            for (; i + 8 <= n; i += 8) {
+                double w8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) w8[u] = wp[(int64_t)(i + u) * ld];
+#pragma unroll
+                for (int u = 0; u < 8; u += 4) {
+                    a0 = fma(s_col[i + u], w8[u], a0);
+                    a1 = fma(s_col[i + u + 1], w8[u + 1], a1);
+                    a2 = fma(s_col[i + u + 2], w8[u + 2], a2);
+                    a3 = fma(s_col[i + u + 3], w8[u + 3], a3);
+                }
+            }
+            if (i < n) {
+                double w8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) w8[u] = i + u < n ? wp[(int64_t)(i + u) * ld] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; u += 4) {
+                    a0 = fma(i + u < n ? s_col[i + u] : 0.0, w8[u], a0);
+                    a1 = fma(i + u + 1 < n ? s_col[i + u + 1] : 0.0, w8[u + 1], a1);
+                    a2 = fma(i + u + 2 < n ? s_col[i + u + 2] : 0.0, w8[u + 2], a2);
+                    a3 = fma(i + u + 3 < n ? s_col[i + u + 3] : 0.0, w8[u + 3], a3);
+                }
+            }
+            const double a = (a0 + a1) + (a2 + a3);
             double k = 0.0;
 #pragma unroll
             for (int q = 0; q < GPX_MAX_DIM; ++q)
                 if (q < kp.d) kacc_dim<FAM>(k, kp, q, s_xp[q], X[q * ld + col]);
             const double w = (kfinish<FAM>(k, kp) - a) / lnn;
             W[(int64_t)n * ld + col] = w;
-            var[col] -= w * w;
+            const double nv = var_old - w * w;
+            var[col] = nv;
+            if (!cside) vpart += nv;
         }
+        const double vsum = small_block_sum(vpart, sm);
+        if (tid == 0) blk_base[b] = vsum;
         grid.sync();
-        // ---- phase C: cov -= w_M[n] w_C[n]^T and the column sums of squares of the next step ----------------------------
+        // ---- phase C: cov -= w_M[n] w_C[n]^T and the column sums of squares of the next step (layout of gpx_cov_update) --
+        part = 0.0;
+        for (int64_t q = tid; q < nb; q += 256) part += __ldcg(blk_base + q);   // consumed after the covariance pass
         const double* am = s.Wm + (int64_t)n * s.ldm;
         const double* bc = s.Wc + (int64_t)n * s.ldc;
-        for (int64_t item = b; item < (int64_t)s.nseg * colchunks; item += nb) {
-            const int64_t seg = item / colchunks, c = (item % colchunks) * 256 + tid;
+        for (int64_t item = b; item < (int64_t)s.nseg * colblocks; item += nb) {
+            const int64_t seg = item / colblocks, c = ((item % colblocks) * 256 + tid) * 2;
             if (c >= C) continue;
             const int64_t m0 = seg * rows_per_seg;
             const int64_t m1 = m0 + rows_per_seg < M ? m0 + rows_per_seg : M;
-            const double bcol = bc[c];
-            double r = 0.0;
+            const double2 bb = *reinterpret_cast<const double2*>(bc + c);
+            double r0 = 0.0, r1 = 0.0;
             double* cp = s.cov + m0 * s.ldcov + c;
-            for (int64_t m = m0; m < m1; ++m, cp += s.ldcov) {
-                const double v = fma(-am[m], bcol, *cp);
-                *cp = v;
-                r = fma(v, v, r);
+            int64_t m = m0;
+            for (; m + 8 <= m1; m += 8) {
+                double2 v[8];
+                double a8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    v[u] = *reinterpret_cast<const double2*>(cp + (int64_t)u * s.ldcov);
+                    a8[u] = am[m + u];
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const double a = a8[u];
+                    v[u].x = fma(-a, bb.x, v[u].x);
+                    v[u].y = fma(-a, bb.y, v[u].y);
+                    *reinterpret_cast<double2*>(cp + (int64_t)u * s.ldcov) = v[u];
+                    r0 = fma(v[u].x, v[u].x, r0);
+                    r1 = fma(v[u].y, v[u].y, r1);
+                }
+                cp += 8 * s.ldcov;
             }
-            s.workspace[seg * s.ldp + c] = r;
+            for (; m < m1; ++m, cp += s.ldcov) {
+                double2 v = *reinterpret_cast<const double2*>(cp);
+                const double a = am[m];
+                v.x = fma(-a, bb.x, v.x);
+                v.y = fma(-a, bb.y, v.y);
+                *reinterpret_cast<double2*>(cp) = v;
+                r0 = fma(v.x, v.x, r0);
+                r1 = fma(v.y, v.y, r1);
+            }
+            double* dst = s.workspace + seg * s.ldp + c;
+            dst[0] = r0;
+            if (c + 1 < C) dst[1] = r1;
         }
+        base_sum = small_block_sum(part, sm);
         grid.sync();
     }
 }
@@ -526,6 +631,9 @@ extern "C" int gpx_ivar_greedy_small(gpx_handle h, const gpx_ivar_state* s, int6
     GPX_REQUIRE(s->cov && s->Xm && s->Wm && s->varM && s->Xc && s->Wc && s->varC && s->workspace && s->scores && s->best &&
                     s->idx && s->picks && s->M >= 1 && s->C >= 1 && s->nseg >= 1 && s->ldp >= s->C && s->ldcov >= s->C,
                 GPX_EINVAL, "the one-kernel loop needs a complete resident state");
+    GPX_REQUIRE((s->ldcov % 2) == 0 && s->ldcov >= s->C + (s->C & 1) && (s->ldc % 2) == 0 && gpx_aligned16(s->cov) &&
+                    gpx_aligned16(s->Wc),
+                GPX_EALIGN, "cov and W_C must be 16-byte aligned with even leading dimensions");
     GPX_REQUIRE(h->nccl_comm == nullptr || h->comm_size <= 1 || s->rec_all == nullptr, GPX_EINVAL,
                 "the one-kernel loop is single-GPU");
     if (n_end == n_begin) return GPX_OK;
@@ -537,14 +645,15 @@ extern "C" int gpx_ivar_greedy_small(gpx_handle h, const gpx_ivar_state* s, int6
         if (e == cudaSuccess) {                                                                                          \
             if (per_sm > 2) per_sm = 2;                                                                                  \
             int blocks = per_sm * (h->sm_count > 0 ? h->sm_count : 148);                                                 \
-            if (blocks > 1024) blocks = 1024;                                                                            \
+            if (blocks > 512) blocks = 512;                                                                              \
             KParams kp = h->kp;                                                                                          \
             gpx_ivar_state st = *s;                                                                                      \
             int nb0 = (int)n_begin, ne0 = (int)n_end;                                                                    \
             double* bv = h->red_val;                                                                                     \
             int64_t* bi = h->red_idx;                                                                                    \
-            double* bp = h->red_val + 1024;                                                                              \
-            void* args[] = {&kp, &st, &nb0, &ne0, &bv, &bi, &bp};                                                        \
+            double* bp = h->red_val + 512;                                                                               \
+            double* bb = h->red_val + 1024;                                                                              \
+            void* args[] = {&kp, &st, &nb0, &ne0, &bv, &bi, &bp, &bb};                                                   \
             e = blocks > 0 ? cudaLaunchCooperativeKernel((const void*)ivar_small_greedy_kernel<F>, dim3(blocks), dim3(256), \
                                                          args, 0, (cudaStream_t)stream)                                  \
                            : cudaErrorLaunchOutOfResources;                                                              \

@@ -157,7 +157,14 @@ class Device:
         if n:
             raw = self.upload(pts)
             check(lib.gpx_transpose(self.h, ptr(raw), n, d, d, ptr(X), ld, self.stream), "gpx_transpose")
-            lo, hi = pts.min(axis=0), pts.max(axis=0)
+            if n * d >= 50_000:
+                # the bounding box from the device copy (numpy's axis-0 reduction of an (n, small d) array costs
+                # milliseconds at 1e5 points): two row reductions and one 2*d-double read-back
+                lo_hi = torch.stack(torch.aminmax(X[:d, :n], dim=1)).cpu().numpy()
+                lo, hi = lo_hi[0], lo_hi[1]
+            else:
+                lo = np.array([pts[:, q].min() for q in range(d)])
+                hi = np.array([pts[:, q].max() for q in range(d)])
         return PointSet(self, X, n, d, lo, hi)
 
     def sync(self) -> None:

@@ -516,7 +516,7 @@ class GreedyIVAREngine(_Pivoting):
     # resident problems up to this many (integration point, candidate) pairs run their whole loop as ONE cooperative
     # kernel (gpx_ivar_greedy_small): 256 MB of covariance, roughly what stays close to the 126 MB L2.
     # GPX_ONE_KERNEL_PAIRS overrides (0 = always the multi-launch loop).
-    ONE_KERNEL_DEFAULT = 0
+    ONE_KERNEL_DEFAULT = 32_000_000
     ONE_KERNEL_PAIRS = int(os.environ.get("GPX_ONE_KERNEL_PAIRS", ONE_KERNEL_DEFAULT))
 
     def __init__(self, dev: Device, cand: PointSet, mc: PointSet, n_max: int, noise: float, zero_scale: float,
