@@ -383,7 +383,7 @@ extern "C" int gpx_sum(gpx_handle h, const double* v, int64_t n, double* out, vo
 
 // ---------------------------------------------------------------------------------------------
 // K3+K4 incremental row append.  Two adjacent columns per thread (16-byte streaming loads), the pivot's
-// W-column in shared memory, 8 independent loads in flight per thread.  Reads 8*n*ncols bytes.
+// W-column in shared memory, 16 independent loads in flight per thread (gpx_append_two_columns).  Reads 8*n*ncols bytes.
 // ---------------------------------------------------------------------------------------------
 template <int FAM, int SRC, int NT>
 __global__ void __launch_bounds__(NT) append_row_kernel(const __grid_constant__ KParams kp, const double* __restrict__ rec,
@@ -391,67 +391,8 @@ __global__ void __launch_bounds__(NT) append_row_kernel(const __grid_constant__ 
                                                           int64_t ncols, int64_t ldy, double* __restrict__ W, int64_t ldw,
                                                           int n, double* __restrict__ var) {
     extern __shared__ double sl[];
-    for (int i = threadIdx.x; i < n; i += NT) sl[i] = rec[GPX_PIVOT_HDR + i];
-    __syncthreads();
     const int64_t j = ((int64_t)blockIdx.x * NT + threadIdx.x) * 2;
-    if (j >= ncols) return;
-    const double* wp = W + j;
-    double a0 = 0.0, a1 = 0.0;
-    int i = 0;
-    for (; i + 16 <= n; i += 16) {
-        double2 w[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) w[u] = __ldcs(reinterpret_cast<const double2*>(wp + (int64_t)(i + u) * ldw));
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            a0 = fma(sl[i + u], w[u].x, a0);
-            a1 = fma(sl[i + u], w[u].y, a1);
-        }
-    }
-    for (; i + 4 <= n; i += 4) {
-        double2 w[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) w[u] = __ldcs(reinterpret_cast<const double2*>(wp + (int64_t)(i + u) * ldw));
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            a0 = fma(sl[i + u], w[u].x, a0);
-            a1 = fma(sl[i + u], w[u].y, a1);
-        }
-    }
-    for (; i < n; ++i) {
-        const double2 w = __ldcs(reinterpret_cast<const double2*>(wp + (int64_t)i * ldw));
-        a0 = fma(sl[i], w.x, a0);
-        a1 = fma(sl[i], w.y, a1);
-    }
-    double s0, s1;
-    if (SRC == GPX_ROW_KERNEL) {
-        double k0 = 0.0, k1 = 0.0;
-#pragma unroll
-        for (int q = 0; q < GPX_MAX_DIM; ++q)
-            if (q < kp.d) {
-                const double xp = rec[3 + q];
-                const double2 y = *reinterpret_cast<const double2*>(Y + q * ldy + j);
-                kacc_dim<FAM>(k0, kp, q, xp, y.x);
-                kacc_dim<FAM>(k1, kp, q, xp, y.y);
-            }
-        s0 = kfinish<FAM>(k0, kp);
-        s1 = kfinish<FAM>(k1, kp);
-    } else {
-        const double2 s = *reinterpret_cast<const double2*>(src_row + j);
-        s0 = s.x;
-        s1 = s.y;
-    }
-    // a non-positive pivot (numerically dependent point, noise 0) appends a zero row: "no reduction", what the
-    // reference's pinv makes of a null direction (gp.py:181) -- instead of NaN from sqrt of a negative number
-    const double lnn = rec[2] > 0.0 ? sqrt(rec[2]) : INFINITY;
-    const double w0 = (s0 - a0) / lnn;
-    const double w1 = (s1 - a1) / lnn;
-    const bool two = j + 1 < ncols;
-    double* dst = W + (int64_t)n * ldw + j;
-    dst[0] = w0;
-    dst[1] = two ? w1 : 0.0;
-    var[j] -= w0 * w0;
-    if (two) var[j + 1] -= w1 * w1;
+    gpx_append_two_columns<FAM, SRC == GPX_ROW_KERNEL>(kp, rec, src_row, Y, ncols, ldy, W, ldw, n, var, j, sl, NT);
 }
 
 extern "C" int gpx_append_row(gpx_handle h, int row_source, const double* rec, const double* src_row, const double* Y,
@@ -470,7 +411,7 @@ extern "C" int gpx_append_row(gpx_handle h, int row_source, const double* rec, c
     } else {
         GPX_REQUIRE(src_row != nullptr && gpx_aligned16(src_row), GPX_EALIGN, "src_row must be 16-byte aligned");
     }
-    const size_t smem = (size_t)n * sizeof(double);
+    const size_t smem = (size_t)((n + 15) / 16 * 16) * sizeof(double);
     GPX_REQUIRE(smem <= 200 * 1024, GPX_ESIZE, "design size exceeds the shared-memory column buffer (25600)");
     cudaStream_t st = (cudaStream_t)stream;
     // 256 columns per 128-thread block.  (Measured in round 2: 64-thread blocks for narrow problems change nothing --

@@ -108,6 +108,95 @@ __device__ __forceinline__ double kfinish(double acc, const KParams& kp) {
     return kp.signal * exp(-acc);
 }
 
+// ---------------------------------------------------------------------------------------------
+// One new factor row for two adjacent columns j, j+1 (K3+K4):  w = (src - sum_i l[i] W[i, j]) / sqrt(pivot).
+// Called by every thread of the block (it holds the block's barrier); sl = shared buffer of roundup(n, 16) doubles that
+// receives the pivot's column l (zero padded).  Ordering is what the timing rests on: the first 16 rows of W are
+// requested BEFORE the pivot column is staged and the source term k(x_p, y_j) evaluated, so their latency is hidden;
+// every later batch is 16 independent 16-byte streaming loads; the ragged end of n is one more predicated batch, not a
+// chain of short ones.  SRC_KERNEL: src from the kernel function of rec's coordinates and Y; else from src_row.
+// ---------------------------------------------------------------------------------------------
+template <int FAM, bool SRC_KERNEL>
+__device__ __forceinline__ void gpx_append_two_columns(const KParams& kp, const double* __restrict__ rec,
+                                                       const double* __restrict__ src_row, const double* __restrict__ Y,
+                                                       int64_t ncols, int64_t ldy, double* __restrict__ W, int64_t ldw, int n,
+                                                       double* __restrict__ var, int64_t j, double* sl, int nthreads) {
+    const bool active = j < ncols;
+    const bool two = j + 1 < ncols;
+    const double* wp = W + j;
+    double2 w[16];
+    double v0 = 0.0, v1 = 0.0;
+    if (active) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+            w[u] = u < n ? __ldcs(reinterpret_cast<const double2*>(wp + (int64_t)u * ldw)) : make_double2(0.0, 0.0);
+        v0 = var[j];
+        if (two) v1 = var[j + 1];
+    }
+    const int n16 = (n + 15) & ~15;
+    for (int i = threadIdx.x; i < n16; i += nthreads) sl[i] = i < n ? rec[GPX_PIVOT_HDR + i] : 0.0;
+    double s0 = 0.0, s1 = 0.0;
+    if (active) {
+        if (SRC_KERNEL) {
+            double k0 = 0.0, k1 = 0.0;
+#pragma unroll
+            for (int q = 0; q < GPX_MAX_DIM; ++q)
+                if (q < kp.d) {
+                    const double xp = rec[3 + q];
+                    const double2 y = *reinterpret_cast<const double2*>(Y + q * ldy + j);
+                    kacc_dim<FAM>(k0, kp, q, xp, y.x);
+                    kacc_dim<FAM>(k1, kp, q, xp, y.y);
+                }
+            s0 = kfinish<FAM>(k0, kp);
+            s1 = kfinish<FAM>(k1, kp);
+        } else {
+            const double2 sv = *reinterpret_cast<const double2*>(src_row + j);
+            s0 = sv.x;
+            s1 = sv.y;
+        }
+    }
+    // a non-positive pivot (numerically dependent point, noise 0) appends a zero row: "no reduction", what the
+    // reference's pinv makes of a null direction (gp.py:181) -- instead of NaN from sqrt of a negative number
+    const double lnn = rec[2] > 0.0 ? sqrt(rec[2]) : INFINITY;
+    __syncthreads();
+    if (!active) return;
+    double a0 = 0.0, a1 = 0.0;
+    if (n > 0) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fma(sl[u], w[u].x, a0);
+            a1 = fma(sl[u], w[u].y, a1);
+        }
+    }
+    int i = 16;
+    for (; i + 16 <= n; i += 16) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) w[u] = __ldcs(reinterpret_cast<const double2*>(wp + (int64_t)(i + u) * ldw));
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fma(sl[i + u], w[u].x, a0);
+            a1 = fma(sl[i + u], w[u].y, a1);
+        }
+    }
+    if (i < n) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+            w[u] = i + u < n ? __ldcs(reinterpret_cast<const double2*>(wp + (int64_t)(i + u) * ldw)) : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fma(sl[i + u], w[u].x, a0);
+            a1 = fma(sl[i + u], w[u].y, a1);
+        }
+    }
+    const double w0 = (s0 - a0) / lnn;
+    const double w1 = (s1 - a1) / lnn;
+    double* dst = W + (int64_t)n * ldw + j;
+    dst[0] = w0;
+    dst[1] = two ? w1 : 0.0;
+    var[j] = v0 - w0 * w0;
+    if (two) var[j + 1] = v1 - w1 * w1;
+}
+
 // 2^(j/256): table-driven exp used by the covariance prologue of the hot kernel and by the Gram kernel.  exp(x) = 2^k * T[j] * e^r with
 // n = rint(x * 256/ln2) = 256 k + j and |r| <= ln2/512, e^r - 1 by a degree-4 polynomial: 9 FP64-pipe
 // operations and one shared-memory lookup per value, <= 1 ulp (libdevice exp: 19 FP64 + 26 other instructions).

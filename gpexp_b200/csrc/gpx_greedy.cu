@@ -233,60 +233,10 @@ template <int FAM, int NT>
 __global__ void __launch_bounds__(NT) append_row2_kernel(const __grid_constant__ KParams kp, const double* __restrict__ rec,
                                                           AppendSide s0, AppendSide s1, unsigned blocks0, int n) {
     extern __shared__ double sl[];
-    for (int i = threadIdx.x; i < n; i += NT) sl[i] = rec[GPX_PIVOT_HDR + i];
-    __syncthreads();
     const bool first = blockIdx.x < blocks0;
     const AppendSide& s = first ? s0 : s1;
     const int64_t j = ((int64_t)(first ? blockIdx.x : blockIdx.x - blocks0) * NT + threadIdx.x) * 2;
-    if (j >= s.ncols) return;
-    const double* wp = s.W + j;
-    const int64_t ldw = s.ldw;
-    double a0 = 0.0, a1 = 0.0;
-    int i = 0;
-    for (; i + 16 <= n; i += 16) {
-        double2 w[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) w[u] = __ldcs(reinterpret_cast<const double2*>(wp + (int64_t)(i + u) * ldw));
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            a0 = fma(sl[i + u], w[u].x, a0);
-            a1 = fma(sl[i + u], w[u].y, a1);
-        }
-    }
-    for (; i + 4 <= n; i += 4) {
-        double2 w[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) w[u] = __ldcs(reinterpret_cast<const double2*>(wp + (int64_t)(i + u) * ldw));
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            a0 = fma(sl[i + u], w[u].x, a0);
-            a1 = fma(sl[i + u], w[u].y, a1);
-        }
-    }
-    for (; i < n; ++i) {
-        const double2 w = __ldcs(reinterpret_cast<const double2*>(wp + (int64_t)i * ldw));
-        a0 = fma(sl[i], w.x, a0);
-        a1 = fma(sl[i], w.y, a1);
-    }
-    double k0 = 0.0, k1 = 0.0;
-#pragma unroll
-    for (int q = 0; q < GPX_MAX_DIM; ++q)
-        if (q < kp.d) {
-            const double xp = rec[3 + q];
-            const double2 y = *reinterpret_cast<const double2*>(s.Y + q * s.ldy + j);
-            kacc_dim<FAM>(k0, kp, q, xp, y.x);
-            kacc_dim<FAM>(k1, kp, q, xp, y.y);
-        }
-    const double s0v = kfinish<FAM>(k0, kp), s1v = kfinish<FAM>(k1, kp);
-    const double lnn = rec[2] > 0.0 ? sqrt(rec[2]) : INFINITY;  // non-positive pivot -> zero row (see append_row_kernel)
-    const double w0 = (s0v - a0) / lnn;
-    const double w1 = (s1v - a1) / lnn;
-    const bool two = j + 1 < s.ncols;
-    double* dst = s.W + (int64_t)n * ldw + j;
-    dst[0] = w0;
-    dst[1] = two ? w1 : 0.0;
-    s.var[j] -= w0 * w0;
-    if (two) s.var[j + 1] -= w1 * w1;
+    gpx_append_two_columns<FAM, true>(kp, rec, nullptr, s.Y, s.ncols, s.ldy, s.W, s.ldw, n, s.var, j, sl, NT);
 }
 
 int launch_gather_store(gpx_handle h, const double* W, int64_t ldw, int64_t n, const double* var, const double* X, int64_t ldx,
@@ -314,7 +264,7 @@ bool side_ok(const AppendSide& s) {
 
 template <int FAM>
 int launch_append2_fam(gpx_handle h, const double* rec, const AppendSide& s0, const AppendSide& s1, int64_t n, cudaStream_t st) {
-    const size_t smem = (size_t)n * sizeof(double);
+    const size_t smem = (size_t)((n + 15) / 16 * 16) * sizeof(double);
     if (smem > 48 * 1024) {
         int rc = gpx_ensure_smem(h, (const void*)append_row2_kernel<FAM, 128>, 200 * 1024, "append_row2");
         if (rc) return rc;
