@@ -1,17 +1,9 @@
-"""Fused Gram/TRSM (gpx_trsm_gram) and its forward-substitution kernel: CUDA-event times at n = 255 and n = 1024 over
-1e5 columns, checked against a float64 torch triangular solve.  GPX_TRI_VARIANT (when the library has the switch)
-selects the block shape of tri_solve_kernel; run once per value."""
+"""Fused Gram/TRSM (gpx_trsm_gram) with its forward-substitution kernel: CUDA-event times at n = 255 and n = 1024 over
+1e5 columns, and the residual |U^T W - K(D, X)| on a slice of columns (numpy on the host).  Used in round 2 to choose
+the block shape of tri_solve_kernel (numbers in DESIGN.md section 4)."""
 import json
 import os
-import subprocess
 import sys
-
-if "--child" not in sys.argv:
-    for v in sys.argv[1:] or ["0"]:
-        env = dict(os.environ, GPX_TRI_VARIANT=v)
-        r = subprocess.run([sys.executable, __file__, "--child"], env=env, capture_output=True, text=True)
-        print("variant", v, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-400:], flush=True)
-    sys.exit(0)
 
 import numpy as np
 import torch
