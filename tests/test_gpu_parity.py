@@ -487,6 +487,41 @@ def test_cfg2_mid_size_greedy_ivar_vs_oracle(gx):
     assert np.max(np.abs(cf.lastScores - want) / np.abs(want)) <= 1e-9
 
 
+def test_cfg2_full_size_step_properties(gx):
+    """BASELINE configs[1] at full size (100 000 candidates x 100 000 integration points, 2-D ARD, n = 255): one
+    scoring step through the public call.  The oracle checks a sample of candidates (with the arg-min); the rest of
+    the full-size result is pinned by size-independent properties of the criterion: a candidate's cost does not depend
+    on where it sits in the candidate array (bit-exact under a permutation), and the integrated variance is additive
+    over a partition of the integration points: M cost(M) = M1 cost(M1) + M2 cost(M2)."""
+    rng = np.random.default_rng(22)
+    C = M = 100_000
+    n, noise = 255, 1e-6
+    cand, mc = rng.uniform(-1, 1, (C, 2)), rng.uniform(-1, 1, (M, 2))
+    design = cand[rng.permutation(C)[:n]]
+    ks, k = spec("se_ard_2d"), product_kernel("se_ard_2d")
+
+    def cost_fn(points):
+        return gx.ed.costFunctionGP_IVAR(gx.gp.GP(k, noise), 1, gx.Space(2, None, None), mcPoints=points)
+
+    costs, best = gx.ed.scoreCandidatesIVAR(cost_fn(mc), design, cand)
+    assert costs.shape == (C,) and np.all(np.isfinite(costs)) and costs[best] == costs.min()
+    sub = np.unique(np.concatenate([[best], rng.permutation(C)[:96]]))
+    w_m, var_m = orc.fast_design_state(ks, design, mc, noise)
+    w_c, var_c = orc.fast_design_state(ks, design, cand[sub], noise)
+    ref = orc.fast_ivar_scores(ks, cand[sub], mc, w_m, var_m, w_c, var_c, noise)
+    assert np.max(np.abs(costs[sub] - ref) / np.abs(ref)) <= 1e-9
+    # position independence
+    perm = rng.permutation(C)
+    costs_p, best_p = gx.ed.scoreCandidatesIVAR(cost_fn(mc), design, cand[perm])
+    assert np.array_equal(costs_p, costs[perm])
+    assert costs_p[best_p] == costs[best]
+    # additivity over the integration points (unequal parts, neither a multiple of the 128-row tile)
+    m1 = 37_411
+    c1, _ = gx.ed.scoreCandidatesIVAR(cost_fn(mc[:m1]), design, cand)
+    c2, _ = gx.ed.scoreCandidatesIVAR(cost_fn(mc[m1:]), design, cand)
+    np.testing.assert_allclose(m1 * c1 + (M - m1) * c2, M * costs, rtol=1e-11, atol=0)
+
+
 def test_cfg5_shape_step_vs_oracle_subset(gx):
     """cfg-5 operand shape (10-D ARD, long K loop, several M-splits) at n = 1024: one scoring step from a given
     design; every 300th candidate and the arg-min are checked against the oracle."""
