@@ -16,8 +16,9 @@ from gpexp_b200.engine import DesignFactor, GreedyIVAREngine, prior_scale  # noq
 
 rng = np.random.default_rng(2)
 pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
-cand_h, mc_h = pin(rng.uniform(-1, 1, (100_000, 2))), pin(rng.uniform(-1, 1, (100_000, 2)))
-design_h = pin(cand_h[rng.permutation(100_000)[:255]])
+C_LOCAL = int(os.environ.get("E2E_CANDIDATES", "100000"))  # 12500 = one rank's share of cfg-2 on 8 GPUs
+cand_h, mc_h = pin(rng.uniform(-1, 1, (C_LOCAL, 2))), pin(rng.uniform(-1, 1, (100_000, 2)))
+design_h = pin(cand_h[rng.permutation(C_LOCAL)[:255]])
 kern = kernels.KernelSquaredExponential([0.06, 0.09], 1.0, 2)
 cf = ed.costFunctionGP_IVAR(gp.GP(kern, 1e-6), 1, Space(2, None, None), mcPoints=mc_h)
 dev = Device.get(0)
