@@ -150,6 +150,48 @@ def _ref_kind():
     return _REF["kind"]
 
 
+def run_reference_configs():
+    """CPU legs of BASELINE configs[2] and configs[3] (plan items iii and iv): the UNMODIFIED reference on
+    bounded samples -- performGreedyVarExperimentalDesign on 20 000 of the cfg-3 candidates for 16 points, and
+    costFunctionGP_MI.evaluate at |V| = 400 of the cfg-4 pool.  One JSON line; baselines, not targets."""
+    import contextlib
+    import io
+    import warnings
+    warnings.filterwarnings("ignore")
+    path = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(path, "gpExp")):
+        print(json.dumps({"unavailable": "baseline/_ref is not staged"}))
+        return
+    sys.path.insert(0, path)
+    import gpExp.experimentalDesign as red
+    import gpExp.gp as rgp
+    import gpExp.kernels as rk
+    from gpExp.approximation import Space
+    out = {"cores": os.cpu_count(), "kind": "reference"}
+    rng = np.random.default_rng(3)
+    pool = rng.uniform(-1, 1, (20_000, 5))
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        red.performGreedyVarExperimentalDesign(rk.KernelIsoMatern(1.0, 1.0, 5), pool, 16, 5)
+    t = time.perf_counter() - t0
+    out["cfg3"] = {"candidates_per_s_per_step": 20_000 * 16 / t, "seconds": t,
+                   "sample": "performGreedyVarExperimentalDesign, 5-D Matern rho=1, 16 points from 20 000 candidates "
+                             "(cost per step grows with the design size; cfg-3 runs to 1 024 points from 250 000)"}
+    rng = np.random.default_rng(4)
+    V = 400
+    pts = rng.standard_normal((V, 3))
+    gp = rgp.GP(rk.KernelMehlerND([0.9, 0.9, 0.9], 3), 1e-2)
+    cf = red.costFunctionGP_MI(gp, 8, Space(3, None, None, noise=None), nmc=V, mcpoints=pts)
+    t0 = time.perf_counter()
+    for i in range(1, 31):
+        cf.evaluate(i, [0])
+    t = time.perf_counter() - t0
+    out["cfg4"] = {"candidates_per_s_per_step": 30 / t, "seconds": t, "V": V,
+                   "sample": "costFunctionGP_MI.evaluate, 3-D Mehler t=0.9, |V| = 400, 30 candidates of one greedy step "
+                             "(two pinv of O(|V|^3) per candidate; cfg-4 has |V| = 200 000)"}
+    print(json.dumps(out))
+
+
 # ---------------------------------------------------------------------------------------------
 # clocks sampler
 # ---------------------------------------------------------------------------------------------
@@ -732,6 +774,13 @@ def run_ours(args):
                   "gram_gbs": gram_gbs, "gram_frac_of_measured_hbm": gram_gbs / hbm, "gram_block": [nx, cand.n],
                   "append_row_gbs": app_gbs, "append_row_frac_of_measured_hbm": app_gbs / hbm, "hbm_peak_gbs": hbm,
                   "hbm_peak_source": hbm_src}
+    if world == 1 and not args.no_cpu and not args.no_configs:
+        try:  # CPU legs of cfg-3 / cfg-4 (the unmodified reference, bounded samples) in a fresh process
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-configs"], capture_output=True,
+                               text=True, timeout=300, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+            extras["cpu_reference_other_configs"] = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:
+            extras["cpu_reference_other_configs"] = {"unavailable": str(e)}
     if cfg5 is not None:
         extras["cfg5"] = cfg5
     if cfg3 is not None:
@@ -769,7 +818,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-configs"])
     ap.add_argument("--ref-procs", type=int, default=32, help="worker processes of the reference arm (capped at the core count)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-parity", action="store_true", help="skip the N>1 parity block")
@@ -781,6 +830,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-configs":
+        run_reference_configs()
     else:
         run_ours(args)
     real_stdout.flush()
