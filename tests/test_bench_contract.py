@@ -37,3 +37,20 @@ def test_reference_arm_other_ranks_stay_silent():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "0"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_cpu_legs_of_the_other_configs_print_one_json_line():
+    """`--impl reference-configs` (called by the GPU arm at N = 1): bounded samples of cfg-1 / cfg-3 / cfg-4 through the
+    staged unmodified reference, or one line saying it is not staged."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference-configs"], capture_output=True,
+                         text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "gpExp")):
+        assert "unavailable" in d
+        return
+    assert d["kind"] == "reference" and d["cores"] >= 1
+    for cfg in ("cfg1", "cfg3", "cfg4"):
+        assert d[cfg]["candidates_per_s_per_step"] > 0 and d[cfg]["seconds"] < 120 and d[cfg]["sample"]
